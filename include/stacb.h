@@ -1,0 +1,136 @@
+/*
+ * stacb.h -- C ABI of the B200-native STAC fitting hot path (libstacb.so).
+ *
+ * Drop-in boundary for talmolab/stac-mjx's solver path.  The reference has no
+ * native plugin interface (it is pure Python over MJX + jaxopt); the seam this
+ * library replaces is the duck-typed solver object and its three drivers:
+ *
+ *   stac_mjx/stac_core.py:175-275   class StacCore { q_opt, m_opt }
+ *   stac_mjx/stac_core.py:27-63     q_loss            -> stacb_loss_grad
+ *   stac_mjx/stac_core.py:66-99     _q_opt            -> stacb_q_opt
+ *   stac_mjx/stac_core.py:102-172   _m_opt            -> stacb_m_stats (+ closed form on the host)
+ *   stac_mjx/utils.py:49-74,147-169 kinematics / replace_qs -> stacb_fk
+ *   stac_mjx/compute_stac.py:17-104   root_optimization  \
+ *   stac_mjx/compute_stac.py:170-278  pose_optimization   > stacb_pose_clips (fused, one launch per pass)
+ *   stac_mjx/stac.py:405-440          the two jax.vmap over clips /
+ *
+ * Conventions
+ *   - plain C types only; every array argument is a DEVICE pointer unless marked host;
+ *     row-major, contiguous, float32 / int32 / uint8, 4-byte aligned.
+ *   - the caller owns every buffer; entry points never allocate (after tree creation),
+ *     never synchronise, and enqueue on the caller's stream (`stream` is a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).
+ *   - return value: 0 on success, negative on error (STACB_E_*); stacb_last_error()
+ *     returns a thread-local message for the last failing call.
+ *   - handles are immutable after creation: entry points are re-entrant.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * All arithmetic is float32 in a fixed ("canonical") operation order documented in
+ * DESIGN.md, so results are reproducible bit-for-bit across launches, grid shapes and GPUs.
+ */
+#ifndef STACB_H_
+#define STACB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STACB_VERSION 100
+
+#define STACB_OK 0
+#define STACB_E_INVALID (-1)     /* bad argument / unsupported model feature */
+#define STACB_E_CUDA (-2)        /* CUDA runtime error (see stacb_last_error) */
+#define STACB_E_UNSUPPORTED (-3) /* model too large for the compiled kernel variants */
+
+/* mujoco.mjtJoint */
+#define STACB_JNT_FREE 0
+#define STACB_JNT_BALL 1
+#define STACB_JNT_SLIDE 2
+#define STACB_JNT_HINGE 3
+
+/* Host-side model description: the MjModel fields the path reads
+ * (reference stac.py:113-133,219-235; MJX smooth.kinematics).  All HOST pointers. */
+typedef struct {
+  int32_t nbody, nq, njnt, nsite;  /* nsite = K keypoint sites */
+  const int32_t *body_parent;      /* [nbody], body 0 = world */
+  const int32_t *body_jntadr;      /* [nbody], -1 if none */
+  const int32_t *body_jntnum;      /* [nbody] */
+  const float *body_pos;           /* [nbody,3] (already scaled, rescale.py:24-25) */
+  const float *body_quat;          /* [nbody,4] w,x,y,z */
+  const int32_t *jnt_type;         /* [njnt] */
+  const int32_t *jnt_qposadr;      /* [njnt] */
+  const int32_t *jnt_bodyid;       /* [njnt] */
+  const float *jnt_pos;            /* [njnt,3] */
+  const float *jnt_axis;           /* [njnt,3] unit */
+  const float *qpos0;              /* [nq] */
+  const int32_t *site_body;        /* [K] body id of each keypoint site, keypoint order
+                                      (= mj_model.site_bodyid[site_idxs], stac_core.py:146) */
+} stacb_tree_desc;
+
+typedef struct stacb_tree stacb_tree;
+
+/* Parse the tree once, derive the execution schedule and copy it to `device`. */
+int stacb_tree_create(const stacb_tree_desc *host_desc, int device, stacb_tree **out);
+void stacb_tree_destroy(stacb_tree *tree);
+
+/* Bytes of dynamic shared memory per chain (warp) the solver kernel uses; informational. */
+int stacb_tree_smem_per_chain(const stacb_tree *tree);
+
+/* utils.kinematics + get_site_xpos for B independent qpos.
+ *   qpos [B,nq]  site_pos [K,3]
+ *   qpos_out [B,nq] (free/ball quaternions normalised, as MJX writes them back)  may be NULL
+ *   xpos [B,nbody,3]  xquat [B,nbody,4]  site_xpos [B,K,3]                         may be NULL */
+int stacb_fk(const stacb_tree *tree, const float *qpos, const float *site_pos, float *qpos_out, float *xpos,
+             float *xquat, float *site_xpos, int B, void *stream);
+
+/* stac_core.q_loss and d loss / d q for B independent (q, q0, kp) triples.
+ *   q, q0 [B,nq]  kp [B,3K]  q_mask [nq] u8  kp_mask [3K] u8  site_pos [K,3]
+ *   loss [B]  grad [B,nq] (NULL to skip the reverse sweep) */
+int stacb_loss_grad(const stacb_tree *tree, const float *q, const float *q0, const float *kp, const uint8_t *q_mask,
+                    const uint8_t *kp_mask, const float *site_pos, float *loss, float *grad, int B, void *stream);
+
+/* stac_core._q_opt: B independent box-constrained FISTA solves (jaxopt 0.8.5 ProjectedGradient
+ * defaults: backtracking line search, maxls halvings, decrease_factor 0.5, acceleration).
+ *   q0 [B,nq]  kp [B,3K]  q_mask [nq]  kp_mask [3K]  lb, ub [nq]
+ *   params [B,nq] (= res.params)  error [B] (= res.state.error)  iters [B]  ls_evals [B] */
+int stacb_q_opt(const stacb_tree *tree, const float *q0, const float *kp, const uint8_t *q_mask, const uint8_t *kp_mask,
+                const float *site_pos, const float *lb, const float *ub, float tol, int maxiter, int maxls, float *params,
+                float *error, int32_t *iters, int32_t *ls_evals, int B, void *stream);
+
+/* Fused root_optimization (frame 0, optional) + pose_optimization over C independent clips of F
+ * frames: one persistent kernel, one warp per clip chain, frames strictly sequential inside.
+ *   kp [C,F,3K]
+ *   qpos_io [C,nq]   in: mjx_data.qpos on entry of each clip;  out: qpos after the last frame
+ *   part_masks [P,nq] u8 (INDIVIDUAL_PART_OPTIMIZATION masks, stac.py:161-183), P may be 0
+ *   do_root, root_kp_idx, trunk_kps [K] u8, root_dims (7 free / 4 slide; compute_stac.py:51-54)
+ *   qpos [C,F,nq]  xpos [C,F,nbody,3]  xquat [C,F,nbody,4]  sites [C,F,K,3]  err [C,F]
+ *   iters, ls_evals [C,F,1+P]  root_stats [C,4] = {iters,ls} of the two root solves
+ *   status [C]: 0 ok, 1 = a non-finite loss was seen in the clip
+ * Any output pointer except qpos may be NULL. */
+int stacb_pose_clips(const stacb_tree *tree, const float *kp, float *qpos_io, const float *site_pos, const float *lb,
+                     const float *ub, const uint8_t *part_masks, int P, int do_root, int root_kp_idx,
+                     const uint8_t *trunk_kps, int root_dims, float tol, int maxiter, int maxls, float *qpos, float *xpos,
+                     float *xquat, float *sites, float *err, int32_t *iters, int32_t *ls_evals, int32_t *root_stats,
+                     int32_t *status, int C, int F, void *stream);
+
+/* _m_opt sufficient statistics over T frames (stac_core.py:146-159):
+ *   s[k,i] = sum_t sum_j R_tk[j,i] (y_tk[j] - p_tk[j]),   z2 = sum_t sum_k |y_tk - p_tk|^2.
+ *   kp [T,3K]  q [T,nq]  scratch [T,3K+1] (per-frame contributions)  s [K,3]  z2 [1]
+ * Frames are reduced in index order (deterministic).  Ranks of a multi-GPU fit call this on
+ * their frame shard and all-reduce (s, z2, T) before applying the closed form. */
+int stacb_m_stats(const stacb_tree *tree, const float *kp, const float *q, float *scratch, float *s, float *z2, int T,
+                  void *stream);
+
+/* Measurement helper for bench.py's FP32 roofline denominator: runs a dense FFMA loop
+ * (blocks x threads, `iters` iterations of 16 independent FMAs per thread). out [blocks*threads]. */
+int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream);
+
+const char *stacb_last_error(void);
+int stacb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STACB_H_ */

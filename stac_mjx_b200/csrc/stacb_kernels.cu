@@ -1,0 +1,1002 @@
+// stacb_kernels.cu -- fused STAC solver for sm_100a: kernels + C ABI (include/stacb.h).
+//
+// One warp owns one chain (a clip, or one independent solve) and runs the whole
+// algorithm in registers + a few KB of shared memory:
+//   FK (parent-frame local transforms, pointer-jumping composition)  -> marker sites ->
+//   masked squared residual -> analytic gradient (prefix-scan subtree wrench, Jacobian
+//   transpose per joint) -> FISTA projected-gradient step with backtracking (jaxopt 0.8.5
+//   ProjectedGradient semantics), frames of a clip strictly sequential with warm start.
+// Replaces reference stac_mjx/stac_core.py:27-99 (q_loss/_q_opt), compute_stac.py:17-104,
+// 170-278 (root/pose optimisation loops), stac_core.py:146-159 (m-phase statistics) and the
+// MJX / jaxopt code underneath them.  Compiled with -fmad=false: every fused multiply-add
+// is explicit, so the arithmetic is the canonical order of DESIGN.md section 4.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "stacb.h"
+#include "stacb_math.cuh"
+
+namespace stacb {
+
+constexpr int JMAX = 3;                     // joints per body handled in place
+constexpr int REC = 10 + 12 * JMAX + 1;     // words per body record (odd stride)
+constexpr int R_POS = 0, R_QUAT = 3, R_NJNT = 7, R_PARENT = 8, R_BODY = 9, R_JNT = 10;
+constexpr int J_TYPE = 0, J_ADR = 1, J_POS = 2, J_AXIS = 5, J_REF = 8, J_SA = 9, J_SE = 10, J_STRIDE = 12;
+
+struct DevSet {
+  int n, rounds;
+  const int *rec;  // [n][REC]
+  const int *anc;  // [rounds][n] set-local ancestor index at distance 2^r, -1 if none
+};
+
+struct DevTree {
+  int nbody, nq, njnt, K, spl;
+  DevSet act, full;
+  const int *site_order;  // [K] sorted position -> keypoint index
+  const int *site_eact;   // [K] by sorted position: active-set index of the site's body
+  const int *site_efull;  // [K] by sorted position: full-set index of the site's body
+  int nqp, pqn, npre;     // per-chain shared memory: qbuf[nqp] gbuf[nqp] PQ[pqn*7] Ipre[npre*6]
+};
+
+__host__ __device__ inline int chain_smem_floats(const DevTree &T) { return 2 * T.nqp + 7 * T.pqn + 6 * T.npre; }
+
+struct Chain {
+  const DevTree &T;
+  int lane;
+  float *qbuf, *gbuf, *PQ, *Ipre;
+  __device__ Chain(const DevTree &t, float *base, int ln) : T(t), lane(ln) {
+    qbuf = base;
+    gbuf = qbuf + t.nqp;
+    PQ = gbuf + t.nqp;
+    Ipre = PQ + 7 * t.pqn;
+  }
+};
+
+__device__ __forceinline__ float ldf(const int *p) { return __int_as_float(__ldg(p)); }
+__device__ __forceinline__ V3 ldv3(const int *p) { return mk3(ldf(p), ldf(p + 1), ldf(p + 2)); }
+__device__ __forceinline__ V3 lds3(const float *p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ Q4 lds4(const float *p) { return mk4(p[0], p[1], p[2], p[3]); }
+
+// Per-lane results of the local phase that the reverse sweep needs.
+template <int NB>
+struct Keep {
+  V3 anchor[NB][JMAX];  // joint anchor in the parent frame of its body
+  V3 axis[NB][JMAX];    // joint axis in the parent frame of its body
+  float fnorm[NB];      // divisor of the quaternion normalisation (free / ball joint)
+};
+
+// MJX smooth.kinematics per-body step, evaluated in the parent's frame (canonical order).
+template <int NB, bool KEEP>
+__device__ __forceinline__ void fk_local(const int *__restrict__ r, float *qbuf, V3 &pos, Q4 &quat, Keep<NB> *keep, int slot) {
+  pos = ldv3(r + R_POS);
+  quat = mk4(ldf(r + R_QUAT), ldf(r + R_QUAT + 1), ldf(r + R_QUAT + 2), ldf(r + R_QUAT + 3));
+  const int nj = __ldg(r + R_NJNT);
+#pragma unroll
+  for (int jj = 0; jj < JMAX; jj++) {
+    if (jj < nj) {
+      const int *jr = r + R_JNT + J_STRIDE * jj;
+      const int type = __ldg(jr + J_TYPE), adr = __ldg(jr + J_ADR);
+      const V3 jpos = ldv3(jr + J_POS), jaxis = ldv3(jr + J_AXIS);
+      V3 anchor, axis;
+      if (type == STACB_JNT_FREE) {
+        anchor = lds3(qbuf + adr);
+        axis = mk3(0.f, 0.f, 1.f);
+      } else {
+        anchor = add3(rotate(jpos, quat), pos);
+        axis = rotate(jaxis, quat);
+      }
+      if (KEEP) { keep->anchor[slot][jj] = anchor; keep->axis[slot][jj] = axis; }
+      if (type == STACB_JNT_FREE) {
+        float d;
+        pos = anchor;
+        quat = normalize4(lds4(qbuf + adr + 3), &d);
+        qbuf[adr + 3] = quat.w; qbuf[adr + 4] = quat.x; qbuf[adr + 5] = quat.y; qbuf[adr + 6] = quat.z;
+        if (KEEP) keep->fnorm[slot] = d;
+      } else if (type == STACB_JNT_BALL) {
+        float d;
+        Q4 ql = normalize4(lds4(qbuf + adr), &d);
+        qbuf[adr] = ql.w; qbuf[adr + 1] = ql.x; qbuf[adr + 2] = ql.y; qbuf[adr + 3] = ql.z;
+        if (KEEP) keep->fnorm[slot] = d;
+        quat = qmul(quat, ql);
+        pos = sub3(anchor, rotate(jpos, quat));
+      } else if (type == STACB_JNT_HINGE) {
+        Q4 ql = axis_angle(jaxis, qbuf[adr] - ldf(jr + J_REF));
+        quat = qmul(quat, ql);
+        pos = sub3(anchor, rotate(jpos, quat));
+      } else {  // slide
+        float d = qbuf[adr] - ldf(jr + J_REF);
+        pos = mk3(fmaf(axis.x, d, pos.x), fmaf(axis.y, d, pos.y), fmaf(axis.z, d, pos.z));
+      }
+    }
+  }
+}
+
+// FK over a body set. On return PQ[e*7..] holds the world pose of every set element and
+// P/Q the poses of this lane's slots. Reads the point from ch.qbuf (quaternions normalised in place).
+template <int NB, bool KEEP>
+__device__ __forceinline__ void fk_set(const Chain &ch, const DevSet &S, V3 (&P)[NB], Q4 (&Q)[NB], Keep<NB> *keep) {
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    const int e = ch.lane + 32 * i;
+    if (e < S.n) fk_local<NB, KEEP>(S.rec + (size_t)e * REC, ch.qbuf, P[i], Q[i], keep, i);
+  }
+  for (int r = 0; r < S.rounds; r++) {
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+      const int e = ch.lane + 32 * i;
+      if (e < S.n) {
+        float *o = ch.PQ + 7 * e;
+        o[0] = P[i].x; o[1] = P[i].y; o[2] = P[i].z; o[3] = Q[i].w; o[4] = Q[i].x; o[5] = Q[i].y; o[6] = Q[i].z;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+      const int e = ch.lane + 32 * i;
+      if (e < S.n) {
+        const int a = __ldg(S.anc + r * S.n + e);
+        if (a >= 0) {
+          const float *o = ch.PQ + 7 * a;
+          const V3 pa = lds3(o);
+          const Q4 qa = lds4(o + 3);
+          P[i] = add3(pa, rotate(P[i], qa));
+          Q[i] = qmul(qa, Q[i]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    const int e = ch.lane + 32 * i;
+    if (e < S.n) {
+      float *o = ch.PQ + 7 * e;
+      o[0] = P[i].x; o[1] = P[i].y; o[2] = P[i].z; o[3] = Q[i].w; o[4] = Q[i].x; o[5] = Q[i].y; o[6] = Q[i].z;
+    }
+  }
+  __syncwarp();
+}
+
+// Per-lane marker data: the lane owns sorted site positions lane*spl + i.
+template <int SPL>
+struct Sites {
+  int k[SPL];      // keypoint index, -1 if the slot is empty
+  int eact[SPL], efull[SPL];
+  V3 off[SPL];     // site offset in the body frame (site_pos)
+  V3 kp[SPL];      // observed keypoint
+  V3 km[SPL];      // 0/1 mask per coordinate
+};
+
+template <int SPL>
+__device__ __forceinline__ void sites_init(const Chain &ch, Sites<SPL> &st, const float *__restrict__ site_pos) {
+#pragma unroll
+  for (int i = 0; i < SPL; i++) {
+    const int pos = ch.lane * ch.T.spl + i;
+    st.k[i] = -1; st.eact[i] = 0; st.efull[i] = 0;
+    st.off[i] = mk3(0.f, 0.f, 0.f); st.kp[i] = mk3(0.f, 0.f, 0.f); st.km[i] = mk3(0.f, 0.f, 0.f);
+    if (i < ch.T.spl && pos < ch.T.K) {
+      const int k = __ldg(ch.T.site_order + pos);
+      st.k[i] = k;
+      st.eact[i] = __ldg(ch.T.site_eact + pos);
+      st.efull[i] = __ldg(ch.T.site_efull + pos);
+      if (site_pos) st.off[i] = mk3(__ldg(site_pos + 3 * k), __ldg(site_pos + 3 * k + 1), __ldg(site_pos + 3 * k + 2));
+    }
+  }
+}
+
+template <int SPL>
+__device__ __forceinline__ void sites_load_kp(Sites<SPL> &st, const float *__restrict__ kp) {
+#pragma unroll
+  for (int i = 0; i < SPL; i++)
+    if (st.k[i] >= 0) st.kp[i] = mk3(kp[3 * st.k[i]], kp[3 * st.k[i] + 1], kp[3 * st.k[i] + 2]);
+}
+
+template <int SPL>
+__device__ __forceinline__ void sites_mask_u8(Sites<SPL> &st, const uint8_t *__restrict__ kp_mask /*[3K] or null = ones*/) {
+#pragma unroll
+  for (int i = 0; i < SPL; i++)
+    if (st.k[i] >= 0) {
+      const int k = st.k[i];
+      st.km[i] = kp_mask ? mk3(kp_mask[3 * k] ? 1.f : 0.f, kp_mask[3 * k + 1] ? 1.f : 0.f, kp_mask[3 * k + 2] ? 1.f : 0.f)
+                         : mk3(1.f, 1.f, 1.f);
+    }
+}
+
+template <int SPL>
+__device__ __forceinline__ void sites_mask_kp(Sites<SPL> &st, const uint8_t *__restrict__ per_kp /*[K] or null = ones*/) {
+#pragma unroll
+  for (int i = 0; i < SPL; i++)
+    if (st.k[i] >= 0) {
+      const float m = (!per_kp || per_kp[st.k[i]]) ? 1.f : 0.f;
+      st.km[i] = mk3(m, m, m);
+    }
+}
+
+// Marker sites from the poses in PQ, masked residual, loss; optionally the inclusive prefix of
+// the per-site wrench (force, torque about cref) into Ipre for the reverse sweep.
+template <int SPL, bool FULLSET>
+__device__ __forceinline__ float sites_loss(const Chain &ch, const Sites<SPL> &st, bool need_grad, V3 *site_out /*[SPL] or null*/) {
+  float acc = 0.f;
+  float w[SPL][6];
+  float run[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  V3 cref = mk3(0.f, 0.f, 0.f);
+  if (need_grad) cref = lds3(ch.PQ);
+#pragma unroll
+  for (int i = 0; i < SPL; i++) {
+    if (st.k[i] >= 0) {
+      const float *o = ch.PQ + 7 * (FULLSET ? st.efull[i] : st.eact[i]);
+      const V3 s = add3(lds3(o), rotate(st.off[i], lds4(o + 3)));
+      if (site_out) site_out[i] = s;
+      const V3 res = mk3((st.kp[i].x - s.x) * st.km[i].x, (st.kp[i].y - s.y) * st.km[i].y, (st.kp[i].z - s.z) * st.km[i].z);
+      const float e = fmaf(res.z, res.z, fmaf(res.y, res.y, res.x * res.x));
+      acc = (i == 0) ? e : acc + e;
+      if (need_grad) {
+        const V3 f = mk3(-2.0f * (st.km[i].x * res.x), -2.0f * (st.km[i].y * res.y), -2.0f * (st.km[i].z * res.z));
+        const V3 tq = cross3(sub3(s, cref), f);
+        const float v[6] = {f.x, f.y, f.z, tq.x, tq.y, tq.z};
+#pragma unroll
+        for (int c = 0; c < 6; c++) { run[c] = (i == 0) ? v[c] : run[c] + v[c]; w[i][c] = run[c]; }
+      }
+    }
+  }
+  const float loss = warp_sum(acc);
+  if (need_grad) {
+    float tot[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) tot[c] = run[c];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const float up = __shfl_up_sync(0xffffffffu, tot[c], off);
+        if (ch.lane >= off) tot[c] = tot[c] + up;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const float ex = __shfl_up_sync(0xffffffffu, tot[c], 1);
+#pragma unroll
+      for (int i = 0; i < SPL; i++) {
+        if (st.k[i] >= 0) {
+          const float val = (ch.lane >= 1) ? ex + w[i][c] : w[i][c];
+          ch.Ipre[6 * (ch.lane * ch.T.spl + i) + c] = val;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return loss;
+}
+
+// Reverse sweep: each body lane turns the subtree wrench of its joints into d loss / d qpos.
+template <int NB>
+__device__ __forceinline__ void joint_grads(const Chain &ch, const DevSet &S, const V3 (&P)[NB], const Q4 (&Q)[NB], const Keep<NB> &keep) {
+  const V3 cref = lds3(ch.PQ);
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    const int e = ch.lane + 32 * i;
+    if (e < S.n) {
+      const int *r = S.rec + (size_t)e * REC;
+      const int nj = __ldg(r + R_NJNT), par = __ldg(r + R_PARENT);
+#pragma unroll
+      for (int jj = 0; jj < JMAX; jj++) {
+        if (jj < nj) {
+          const int *jr = r + R_JNT + J_STRIDE * jj;
+          const int type = __ldg(jr + J_TYPE), adr = __ldg(jr + J_ADR), sa = __ldg(jr + J_SA), se = __ldg(jr + J_SE);
+          if (se > sa) {
+            float wr[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+              const float hi = ch.Ipre[6 * (se - 1) + c];
+              wr[c] = (sa > 0) ? hi - ch.Ipre[6 * (sa - 1) + c] : hi;
+            }
+            const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
+            if (type == STACB_JNT_FREE) {
+              const V3 Tp = sub3(Tq, cross3(sub3(P[i], cref), F));
+              ch.gbuf[adr] = F.x; ch.gbuf[adr + 1] = F.y; ch.gbuf[adr + 2] = F.z;
+              const Q4 qh = Q[i];
+              Q4 h = qmul(mk4(0.f, Tp.x, Tp.y, Tp.z), qh);
+              h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
+              const float pr = fmaf(qh.z, h.z, fmaf(qh.y, h.y, fmaf(qh.x, h.x, qh.w * h.w))), n = keep.fnorm[i];
+              ch.gbuf[adr + 3] = fmaf(-qh.w, pr, h.w) / n; ch.gbuf[adr + 4] = fmaf(-qh.x, pr, h.x) / n;
+              ch.gbuf[adr + 5] = fmaf(-qh.y, pr, h.y) / n; ch.gbuf[adr + 6] = fmaf(-qh.z, pr, h.z) / n;
+            } else {
+              V3 A = keep.anchor[i][jj], W = keep.axis[i][jj];
+              if (par >= 0) {
+                const float *o = ch.PQ + 7 * par;
+                const Q4 pq = lds4(o + 3);
+                A = add3(lds3(o), rotate(A, pq));
+                W = rotate(W, pq);
+              }
+              if (type == STACB_JNT_SLIDE) {
+                ch.gbuf[adr] = dot3(W, F);
+              } else {
+                const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
+                if (type == STACB_JNT_HINGE) {
+                  ch.gbuf[adr] = dot3(W, Ta);
+                } else {  // ball (must be the last joint of its body)
+                  const Q4 qb = Q[i];
+                  const V3 tl = rotate(Ta, mk4(qb.w, -qb.x, -qb.y, -qb.z));
+                  const Q4 ql = lds4(ch.qbuf + adr);
+                  Q4 h = qmul(ql, mk4(0.f, tl.x, tl.y, tl.z));
+                  h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
+                  const float pr = fmaf(ql.z, h.z, fmaf(ql.y, h.y, fmaf(ql.x, h.x, ql.w * h.w))), n = keep.fnorm[i];
+                  ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) / n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) / n;
+                  ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) / n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) / n;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Solver-side per-lane state: coordinate i = lane + 32*m lives in slot m.
+template <int CPL>
+struct Coords {
+  float lb[CPL], ub[CPL];
+  bool valid[CPL];
+};
+
+// q_loss at `pt` (stac_core.py:27-63). mask bit m set <=> slot m is optimised; elsewhere q0 is used.
+template <int CPL, int NB, int SPL>
+__device__ __forceinline__ float eval_point(const Chain &ch, const Coords<CPL> &co, const float (&pt)[CPL], const float (&q0)[CPL],
+                                            unsigned maskbits, const Sites<SPL> &st, bool need_grad, float (&g)[CPL]) {
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = ((maskbits >> m) & 1u) ? pt[m] : q0[m];
+  __syncwarp();
+  V3 P[NB];
+  Q4 Q[NB];
+  Keep<NB> keep;
+  fk_set<NB, true>(ch, ch.T.act, P, Q, &keep);
+  const float loss = sites_loss<SPL, false>(ch, st, need_grad, nullptr);
+  if (need_grad) {
+    joint_grads<NB>(ch, ch.T.act, P, Q, keep);
+#pragma unroll
+    for (int m = 0; m < CPL; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? ch.gbuf[ch.lane + 32 * m] : 0.f;
+  }
+  return loss;
+}
+
+template <int CPL>
+__device__ __forceinline__ float lane_dot(const float (&a)[CPL], const float (&b)[CPL]) {
+  float acc = a[0] * b[0];
+#pragma unroll
+  for (int m = 1; m < CPL; m++) acc = fmaf(a[m], b[m], acc);
+  return acc;
+}
+
+struct SolveOut { float err; int iters, ls; bool bad; };
+
+// jaxopt 0.8.5 ProjectedGradient.run (ProximalGradient._update_accel/_ls/_error, box projection).
+template <int CPL, int NB, int SPL>
+__device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co, const float (&q0)[CPL], unsigned maskbits,
+                                          const Sites<SPL> &st, float tol, int maxiter, int maxls, float (&x)[CPL]) {
+  float y[CPL], g[CPL], xn[CPL], d[CPL], gn[CPL];
+#pragma unroll
+  for (int m = 0; m < CPL; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; g[m] = 0.f; gn[m] = 0.f; }
+  float t = 1.0f, step = 1.0f, err = __int_as_float(0x7f800000);
+  SolveOut out;
+  out.iters = 0; out.ls = 0; out.bad = false;
+  if (maxiter <= 0) { out.err = err; return out; }
+  do {
+    const float fy = eval_point<CPL, NB, SPL>(ch, co, y, q0, maskbits, st, true, g);
+    float stp = step;
+    int halv = 0;
+    for (;;) {
+#pragma unroll
+      for (int m = 0; m < CPL; m++) xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      const float fn = eval_point<CPL, NB, SPL>(ch, co, xn, q0, maskbits, st, false, gn);
+      out.ls++;
+#pragma unroll
+      for (int m = 0; m < CPL; m++) d[m] = xn[m] - y[m];
+      const float sq = warp_sum(lane_dot<CPL>(d, d));
+      const float dg = warp_sum(lane_dot<CPL>(d, g));
+      const float dec = stp * (fn - fy);
+      const float cond = fmaf(stp, dg, 0.5f * sq);
+      if (!(fn - fn == 0.0f)) out.bad = true;
+      if (!(dec > cond + 1.1920929e-07f) || halv >= maxls) break;
+      stp = stp * 0.5f;
+      halv++;
+    }
+    step = (stp <= 1e-6f) ? 1.0f : stp / 0.5f;
+    const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+    const float beta = (t - 1.0f) / tn;
+#pragma unroll
+    for (int m = 0; m < CPL; m++) y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
+    eval_point<CPL, NB, SPL>(ch, co, xn, q0, maskbits, st, true, gn);
+#pragma unroll
+    for (int m = 0; m < CPL; m++) d[m] = co.valid[m] ? clipf(xn[m] - gn[m], co.lb[m], co.ub[m]) - xn[m] : 0.f;
+    err = sqrtf(warp_sum(lane_dot<CPL>(d, d)));
+#pragma unroll
+    for (int m = 0; m < CPL; m++) x[m] = xn[m];
+    t = tn;
+    out.iters++;
+  } while (err > tol && out.iters < maxiter);
+  out.err = err;
+  return out;
+}
+
+// replace_qs (utils.py:147-169) as far as qpos is concerned: kinematics normalises free / ball
+// quaternions in place. q holds the full qpos vector of the chain.
+template <int CPL, int NBF>
+__device__ __forceinline__ void normalize_qpos(const Chain &ch, const Coords<CPL> &co, float (&q)[CPL]) {
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = q[m];
+  __syncwarp();
+  const DevSet &S = ch.T.full;
+#pragma unroll
+  for (int i = 0; i < NBF; i++) {
+    const int e = ch.lane + 32 * i;
+    if (e < S.n) {
+      const int *r = S.rec + (size_t)e * REC;
+      const int nj = __ldg(r + R_NJNT);
+      for (int jj = 0; jj < nj && jj < JMAX; jj++) {
+        const int *jr = r + R_JNT + J_STRIDE * jj;
+        const int type = __ldg(jr + J_TYPE);
+        if (type == STACB_JNT_FREE || type == STACB_JNT_BALL) {
+          const int a = __ldg(jr + J_ADR) + (type == STACB_JNT_FREE ? 3 : 0);
+          float dd;
+          const Q4 qn = normalize4(lds4(ch.qbuf + a), &dd);
+          ch.qbuf[a] = qn.w; ch.qbuf[a + 1] = qn.x; ch.qbuf[a + 2] = qn.y; ch.qbuf[a + 3] = qn.z;
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m]) q[m] = ch.qbuf[ch.lane + 32 * m];
+  __syncwarp();
+}
+
+template <int CPL>
+__device__ __forceinline__ void coords_init(const Chain &ch, Coords<CPL> &co, const float *__restrict__ lb, const float *__restrict__ ub) {
+#pragma unroll
+  for (int m = 0; m < CPL; m++) {
+    const int i = ch.lane + 32 * m;
+    co.valid[m] = i < ch.T.nq;
+    co.lb[m] = co.valid[m] && lb ? lb[i] : 0.f;
+    co.ub[m] = co.valid[m] && ub ? ub[i] : 0.f;
+  }
+}
+
+template <int CPL>
+__device__ __forceinline__ unsigned mask_bits_u8(const Chain &ch, const Coords<CPL> &co, const uint8_t *__restrict__ mask /*[nq] or null=all*/) {
+  unsigned b = 0;
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m] && (!mask || mask[ch.lane + 32 * m])) b |= 1u << m;
+  return b;
+}
+
+// Full-model FK of q (normalised in place) and the per-frame outputs.
+template <int CPL, int NBF, int SPL>
+__device__ __forceinline__ void full_outputs(const Chain &ch, const Coords<CPL> &co, float (&q)[CPL], const Sites<SPL> &st,
+                                             float *qpos_o, float *xpos_o, float *xquat_o, float *sites_o) {
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = q[m];
+  __syncwarp();
+  V3 P[NBF];
+  Q4 Q[NBF];
+  fk_set<NBF, false>(ch, ch.T.full, P, Q, nullptr);
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m]) {
+      q[m] = ch.qbuf[ch.lane + 32 * m];
+      if (qpos_o) qpos_o[ch.lane + 32 * m] = q[m];
+    }
+  const DevSet &S = ch.T.full;
+#pragma unroll
+  for (int i = 0; i < NBF; i++) {
+    const int e = ch.lane + 32 * i;
+    if (e < S.n) {
+      const int b = __ldg(S.rec + (size_t)e * REC + R_BODY);
+      if (xpos_o) { xpos_o[3 * b] = P[i].x; xpos_o[3 * b + 1] = P[i].y; xpos_o[3 * b + 2] = P[i].z; }
+      if (xquat_o) { xquat_o[4 * b] = Q[i].w; xquat_o[4 * b + 1] = Q[i].x; xquat_o[4 * b + 2] = Q[i].y; xquat_o[4 * b + 3] = Q[i].z; }
+    }
+  }
+  if (ch.lane == 0) {
+    if (xpos_o) { xpos_o[0] = 0.f; xpos_o[1] = 0.f; xpos_o[2] = 0.f; }
+    if (xquat_o) { xquat_o[0] = 1.f; xquat_o[1] = 0.f; xquat_o[2] = 0.f; xquat_o[3] = 0.f; }
+  }
+  if (sites_o) {
+#pragma unroll
+    for (int i = 0; i < SPL; i++)
+      if (st.k[i] >= 0) {
+        const float *o = ch.PQ + 7 * st.efull[i];
+        const V3 s = add3(lds3(o), rotate(st.off[i], lds4(o + 3)));
+        sites_o[3 * st.k[i]] = s.x; sites_o[3 * st.k[i] + 1] = s.y; sites_o[3 * st.k[i] + 2] = s.z;
+      }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+struct PoseArgs {
+  const float *kp; float *qpos_io; const float *site_pos, *lb, *ub; const uint8_t *part_masks; int P;
+  int do_root, root_kp_idx; const uint8_t *trunk_kps; int root_dims; float tol; int maxiter, maxls;
+  float *qpos, *xpos, *xquat, *sites, *err; int32_t *iters, *ls_evals, *root_stats, *status; int C, F;
+  int *counter;
+};
+
+template <int CPL, int NB, int NBF, int SPL>
+__global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  Chain ch(T, smem + (size_t)wib * chain_smem_floats(T), lane);
+  Coords<CPL> co;
+  coords_init<CPL>(ch, co, a.lb, a.ub);
+  Sites<SPL> st;
+  sites_init<SPL>(ch, st, a.site_pos);
+  const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P;
+  const unsigned full_bits = mask_bits_u8<CPL>(ch, co, nullptr);
+  unsigned root_bits = 0;
+#pragma unroll
+  for (int m = 0; m < CPL; m++)
+    if (co.valid[m] && lane + 32 * m < a.root_dims) root_bits |= 1u << m;
+
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(a.counter, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= a.C) break;
+    for (int m = 0; m < CPL; m++)
+      if (co.valid[m]) ch.gbuf[lane + 32 * m] = 0.f;
+    __syncwarp();
+    float q[CPL], q0[CPL], x[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; m++) q[m] = co.valid[m] ? a.qpos_io[(size_t)c * nq + lane + 32 * m] : 0.f;
+    bool bad = false;
+    const float *kpc = a.kp + (size_t)c * a.F * 3 * K;
+    if (a.do_root) {
+      sites_load_kp<SPL>(st, kpc);
+      sites_mask_kp<SPL>(st, a.trunk_kps);
+      for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+          q0[m] = q[m];
+          const int i = lane + 32 * m;
+          if (i < 3) q0[m] = kpc[3 * a.root_kp_idx + i];
+        }
+        const SolveOut so = solve<CPL, NB, SPL>(ch, co, q0, root_bits, st, a.tol, a.maxiter, a.maxls, x);
+#pragma unroll
+        for (int m = 0; m < CPL; m++) q[m] = ((root_bits >> m) & 1u) ? x[m] : q0[m];
+        normalize_qpos<CPL, NBF>(ch, co, q);
+        bad |= so.bad;
+        if (a.root_stats && lane == 0) { a.root_stats[4 * c + 2 * rep] = so.iters; a.root_stats[4 * c + 2 * rep + 1] = so.ls; }
+      }
+    }
+    sites_mask_kp<SPL>(st, nullptr);
+    for (int f = 0; f < a.F; f++) {
+      sites_load_kp<SPL>(st, kpc + (size_t)f * 3 * K);
+      SolveOut so;
+      const size_t sidx = ((size_t)c * a.F + f) * S1;
+      // stage 0: whole body; stages 1..P: INDIVIDUAL_PART_OPTIMIZATION masks (compute_stac.py:216-250)
+      for (int sg = 0; sg <= a.P; sg++) {
+        const unsigned bits = (sg == 0) ? full_bits : mask_bits_u8<CPL>(ch, co, a.part_masks + (size_t)(sg - 1) * nq);
+#pragma unroll
+        for (int m = 0; m < CPL; m++) q0[m] = q[m];
+        so = solve<CPL, NB, SPL>(ch, co, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
+#pragma unroll
+        for (int m = 0; m < CPL; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];
+        bad |= so.bad;
+        if (a.iters && lane == 0) { a.iters[sidx + sg] = so.iters; a.ls_evals[sidx + sg] = so.ls; }
+        // replace_qs: kinematics normalises the quaternions; the last stage's FK also yields the frame outputs
+        if (sg < a.P) normalize_qpos<CPL, NBF>(ch, co, q);
+      }
+      const size_t fi = (size_t)c * a.F + f;
+      full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
+                                  a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
+      if (a.err && lane == 0) a.err[fi] = so.err;
+    }
+#pragma unroll
+    for (int m = 0; m < CPL; m++)
+      if (co.valid[m]) a.qpos_io[(size_t)c * nq + lane + 32 * m] = q[m];
+    if (a.status && lane == 0) a.status[c] = bad ? 1 : 0;
+  }
+}
+
+struct BatchArgs {
+  const float *q, *q0, *kp, *site_pos, *lb, *ub; const uint8_t *q_mask, *kp_mask; float tol; int maxiter, maxls;
+  float *out_a, *out_b, *out_c, *out_d; int32_t *iters, *ls_evals; int B; int mode;  // 0 fk, 1 loss_grad, 2 q_opt, 3 m_stats
+};
+
+template <int CPL, int NB, int NBF, int SPL>
+__global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  Chain ch(T, smem + (size_t)wib * chain_smem_floats(T), lane);
+  Coords<CPL> co;
+  coords_init<CPL>(ch, co, a.lb, a.ub);
+  Sites<SPL> st;
+  sites_init<SPL>(ch, st, a.site_pos);
+  const int nq = T.nq, K = T.K, nb = T.nbody;
+  const int wpb = blockDim.x >> 5;
+  for (int b = blockIdx.x * wpb + wib; b < a.B; b += gridDim.x * wpb) {
+    float q[CPL], q0[CPL], g[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+      q[m] = co.valid[m] ? a.q[(size_t)b * nq + lane + 32 * m] : 0.f;
+      q0[m] = (co.valid[m] && a.q0) ? a.q0[(size_t)b * nq + lane + 32 * m] : q[m];
+      g[m] = 0.f;
+      if (co.valid[m]) ch.gbuf[lane + 32 * m] = 0.f;
+    }
+    __syncwarp();
+    if (a.mode == 0) {
+      full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.out_a ? a.out_a + (size_t)b * nq : nullptr, a.out_b ? a.out_b + (size_t)b * nb * 3 : nullptr,
+                                  a.out_c ? a.out_c + (size_t)b * nb * 4 : nullptr, a.out_d ? a.out_d + (size_t)b * K * 3 : nullptr);
+    } else if (a.mode == 1) {
+      sites_load_kp<SPL>(st, a.kp + (size_t)b * 3 * K);
+      sites_mask_u8<SPL>(st, a.kp_mask);
+      const unsigned bits = mask_bits_u8<CPL>(ch, co, a.q_mask);
+      const float loss = eval_point<CPL, NB, SPL>(ch, co, q, q0, bits, st, a.out_b != nullptr, g);
+      if (lane == 0) a.out_a[b] = loss;
+      if (a.out_b) {
+#pragma unroll
+        for (int m = 0; m < CPL; m++)
+          if (co.valid[m]) a.out_b[(size_t)b * nq + lane + 32 * m] = g[m];
+      }
+    } else if (a.mode == 2) {
+      sites_load_kp<SPL>(st, a.kp + (size_t)b * 3 * K);
+      sites_mask_u8<SPL>(st, a.kp_mask);
+      const unsigned bits = mask_bits_u8<CPL>(ch, co, a.q_mask);
+      float x[CPL];
+      const SolveOut so = solve<CPL, NB, SPL>(ch, co, q, bits, st, a.tol, a.maxiter, a.maxls, x);
+#pragma unroll
+      for (int m = 0; m < CPL; m++)
+        if (co.valid[m]) a.out_a[(size_t)b * nq + lane + 32 * m] = x[m];
+      if (lane == 0) { a.out_b[b] = so.err; a.iters[b] = so.iters; a.ls_evals[b] = so.ls; }
+    } else {
+      // m-phase per-frame contributions (stac_core.py:148-159): out_a[b][3K+1] = { R^T z per site, |z|^2 }
+      sites_load_kp<SPL>(st, a.kp + (size_t)b * 3 * K);
+#pragma unroll
+      for (int m = 0; m < CPL; m++)
+        if (co.valid[m]) ch.qbuf[lane + 32 * m] = q[m];
+      __syncwarp();
+      V3 P[NB];
+      Q4 Q[NB];
+      fk_set<NB, false>(ch, T.act, P, Q, nullptr);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < SPL; i++) {
+        if (st.k[i] >= 0) {
+          const float *o = ch.PQ + 7 * st.eact[i];
+          const V3 p = lds3(o);
+          const Q4 qb = lds4(o + 3);
+          const V3 z = mk3(st.kp[i].x - p.x, st.kp[i].y - p.y, st.kp[i].z - p.z);
+          // math.quat_to_mat
+          const float ww = qb.w * qb.w, xx = qb.x * qb.x, yy = qb.y * qb.y, zz = qb.z * qb.z;
+          const float xy = qb.x * qb.y, xz = qb.x * qb.z, yz = qb.y * qb.z, wx = qb.w * qb.x, wy = qb.w * qb.y, wz = qb.w * qb.z;
+          const float M00 = ww + xx - yy - zz, M01 = 2.0f * (xy - wz), M02 = 2.0f * (xz + wy);
+          const float M10 = 2.0f * (xy + wz), M11 = ww - xx + yy - zz, M12 = 2.0f * (yz - wx);
+          const float M20 = 2.0f * (xz - wy), M21 = 2.0f * (yz + wx), M22 = ww - xx - yy + zz;
+          float *o3 = a.out_a + (size_t)b * (3 * K + 1) + 3 * st.k[i];
+          o3[0] = fmaf(M20, z.z, fmaf(M10, z.y, M00 * z.x));
+          o3[1] = fmaf(M21, z.z, fmaf(M11, z.y, M01 * z.x));
+          o3[2] = fmaf(M22, z.z, fmaf(M12, z.y, M02 * z.x));
+          const float e = fmaf(z.z, z.z, fmaf(z.y, z.y, z.x * z.x));
+          acc = (i == 0) ? e : acc + e;
+        }
+      }
+      const float z2 = warp_sum(acc);
+      if (lane == 0) a.out_a[(size_t)b * (3 * K + 1) + 3 * K] = z2;
+      __syncwarp();
+    }
+  }
+}
+
+// Sequential (index-order) reduction of the per-frame m-phase contributions: one thread per output.
+__global__ void m_reduce_kernel(const float *__restrict__ contrib, int T, int n3k, float *__restrict__ s, float *__restrict__ z2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n3k) return;
+  float acc = 0.f;
+  for (int t = 0; t < T; t++) acc = acc + contrib[(size_t)t * (n3k + 1) + c];
+  if (c < n3k) s[c] = acc; else z2[0] = acc;
+}
+
+__global__ void fma_peak_kernel(float *out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+  const float m = 0.9999f, c = 1e-4f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace stacb
+
+// ------------------------------------------------------------------------------------------
+// host side: schedule derivation + C ABI
+// ------------------------------------------------------------------------------------------
+
+using namespace stacb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(STACB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct stacb_tree {
+  int device;
+  DevTree T;
+  int cpl, bpl_act, bpl_full;
+  std::vector<void *> allocs;
+  int *counter;
+};
+
+static int ceil_log2(int x) { int r = 0; while ((1 << r) < x) r++; return r; }
+
+template <class V>
+static int upload(stacb_tree *t, const std::vector<V> &h, const V **out) {
+  void *d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(V);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  t->allocs.push_back(d);
+  if (!h.empty()) CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+  *out = (const V *)d;
+  return STACB_OK;
+}
+
+static int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+
+// Body-set records (parents precede children because body ids are DFS pre-order).
+static void build_set(const stacb_tree_desc &m, const std::vector<int> &set, const std::vector<int> &subsize, const std::vector<int> &order,
+                      std::vector<int> &rec, std::vector<int> &anc, int &rounds) {
+  const int n = (int)set.size();
+  std::vector<int> loc(m.nbody, -1), depth(m.nbody, 0);
+  for (int b = 1; b < m.nbody; b++) depth[b] = depth[m.body_parent[b]] + 1;
+  int maxd = 1;
+  for (int e = 0; e < n; e++) { loc[set[e]] = e; maxd = std::max(maxd, depth[set[e]]); }
+  rounds = ceil_log2(maxd);
+  rec.assign((size_t)n * REC, 0);
+  for (int e = 0; e < n; e++) {
+    const int b = set[e];
+    int *r = rec.data() + (size_t)e * REC;
+    for (int c = 0; c < 3; c++) r[R_POS + c] = f2i(m.body_pos[3 * b + c]);
+    for (int c = 0; c < 4; c++) r[R_QUAT + c] = f2i(m.body_quat[4 * b + c]);
+    r[R_NJNT] = m.body_jntnum[b];
+    const int p = m.body_parent[b];
+    r[R_PARENT] = (p != 0) ? loc[p] : -1;
+    r[R_BODY] = b;
+    for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
+      const int j = m.body_jntadr[b] + jj;
+      int *jr = r + R_JNT + J_STRIDE * jj;
+      jr[J_TYPE] = m.jnt_type[j];
+      jr[J_ADR] = m.jnt_qposadr[j];
+      for (int c = 0; c < 3; c++) { jr[J_POS + c] = f2i(m.jnt_pos[3 * j + c]); jr[J_AXIS + c] = f2i(m.jnt_axis[3 * j + c]); }
+      const int t = m.jnt_type[j];
+      jr[J_REF] = f2i((t == STACB_JNT_HINGE || t == STACB_JNT_SLIDE) ? m.qpos0[m.jnt_qposadr[j]] : 0.f);
+      // sorted-site range under this body
+      const int lo = b, hi = b + subsize[b], K = m.nsite;
+      int a = 0;
+      while (a < K && m.site_body[order[a]] < lo) a++;
+      int e2 = a;
+      while (e2 < K && m.site_body[order[e2]] < hi) e2++;
+      jr[J_SA] = a;
+      jr[J_SE] = e2;
+    }
+  }
+  const int nr = std::max(rounds, 1);
+  anc.assign((size_t)nr * n, -1);
+  for (int e = 0; e < n; e++) anc[e] = rec[(size_t)e * REC + R_PARENT];
+  for (int r = 1; r < nr; r++)
+    for (int e = 0; e < n; e++) {
+      const int a = anc[(size_t)(r - 1) * n + e];
+      anc[(size_t)r * n + e] = (a >= 0) ? anc[(size_t)(r - 1) * n + a] : -1;
+    }
+}
+
+extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tree **out) {
+  if (!d || !out) return fail(STACB_E_INVALID, "null argument");
+  const stacb_tree_desc &m = *d;
+  if (m.nbody < 2 || m.nq < 1 || m.njnt < 0 || m.nsite < 1) return fail(STACB_E_INVALID, "empty model");
+  for (int b = 1; b < m.nbody; b++) {
+    if (m.body_parent[b] < 0 || m.body_parent[b] >= b) return fail(STACB_E_INVALID, "body ids must be in depth-first pre-order");
+    if (m.body_jntnum[b] > JMAX) return fail(STACB_E_UNSUPPORTED, "more than 3 joints on one body");
+    for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
+      const int j = m.body_jntadr[b] + jj, t = m.jnt_type[j];
+      if (t == STACB_JNT_FREE && (m.body_parent[b] != 0 || m.body_jntnum[b] != 1))
+        return fail(STACB_E_INVALID, "a free joint must be the only joint of a top-level body");
+      if (t == STACB_JNT_BALL && jj != m.body_jntnum[b] - 1) return fail(STACB_E_UNSUPPORTED, "a ball joint must be the last joint of its body");
+      if (t < 0 || t > 3) return fail(STACB_E_INVALID, "unknown joint type");
+    }
+  }
+  for (int k = 0; k < m.nsite; k++)
+    if (m.site_body[k] <= 0 || m.site_body[k] >= m.nbody) return fail(STACB_E_INVALID, "keypoint site must be attached to a non-world body");
+  CUDA_TRY(cudaSetDevice(device));
+  stacb_tree *t = new stacb_tree();
+  t->device = device;
+  const int nb = m.nbody, K = m.nsite;
+  std::vector<int> subsize(nb, 0);
+  for (int b = nb - 1; b >= 0; b--) { subsize[b] += 1; if (b > 0) subsize[m.body_parent[b]] += subsize[b]; }
+  std::vector<char> isact(nb, 0);
+  for (int k = 0; k < K; k++) { int b = m.site_body[k]; while (b != 0 && !isact[b]) { isact[b] = 1; b = m.body_parent[b]; } }
+  std::vector<int> act, full;
+  for (int b = 1; b < nb; b++) { full.push_back(b); if (isact[b]) act.push_back(b); }
+  std::vector<int> order(K);
+  for (int k = 0; k < K; k++) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m.site_body[a] < m.site_body[b]; });
+  std::vector<int> rec_a, anc_a, rec_f, anc_f;
+  int ra, rf;
+  build_set(m, act, subsize, order, rec_a, anc_a, ra);
+  build_set(m, full, subsize, order, rec_f, anc_f, rf);
+  std::vector<int> loc_a(nb, -1), loc_f(nb, -1), se_a(K), se_f(K);
+  for (size_t e = 0; e < act.size(); e++) loc_a[act[e]] = (int)e;
+  for (size_t e = 0; e < full.size(); e++) loc_f[full[e]] = (int)e;
+  for (int p = 0; p < K; p++) { se_a[p] = loc_a[m.site_body[order[p]]]; se_f[p] = loc_f[m.site_body[order[p]]]; }
+  DevTree &T = t->T;
+  T.nbody = nb; T.nq = m.nq; T.njnt = m.njnt; T.K = K; T.spl = std::max(1, (K + 31) / 32);
+  T.act.n = (int)act.size(); T.act.rounds = ra;
+  T.full.n = (int)full.size(); T.full.rounds = rf;
+  int rc;
+  if ((rc = upload(t, rec_a, &T.act.rec)) || (rc = upload(t, anc_a, &T.act.anc)) || (rc = upload(t, rec_f, &T.full.rec)) ||
+      (rc = upload(t, anc_f, &T.full.anc)) || (rc = upload(t, order, &T.site_order)) || (rc = upload(t, se_a, &T.site_eact)) ||
+      (rc = upload(t, se_f, &T.site_efull))) {
+    stacb_tree_destroy(t);
+    return rc;
+  }
+  t->cpl = (m.nq + 31) / 32; t->bpl_act = (T.act.n + 31) / 32; t->bpl_full = (T.full.n + 31) / 32;
+  T.nqp = 32 * t->cpl; T.pqn = std::max(T.act.n, T.full.n); T.npre = 32 * T.spl;
+  void *cnt = nullptr;
+  if (cudaMalloc(&cnt, sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
+  t->allocs.push_back(cnt);
+  t->counter = (int *)cnt;
+  *out = t;
+  return STACB_OK;
+}
+
+extern "C" void stacb_tree_destroy(stacb_tree *t) {
+  if (!t) return;
+  for (void *p : t->allocs) cudaFree(p);
+  delete t;
+}
+
+extern "C" int stacb_tree_smem_per_chain(const stacb_tree *t) { return t ? chain_smem_floats(t->T) * 4 : 0; }
+
+// kernel variants: (coords per lane, active bodies per lane, all bodies per lane, sites per lane)
+#define STACB_VARIANTS(X) X(1, 1, 1, 1) X(3, 1, 3, 1) X(2, 2, 3, 1) X(4, 3, 4, 2) X(8, 6, 7, 2)
+
+template <int CPL, int NB, int NBF, int SPL>
+static int launch_pose(const stacb_tree *t, const PoseArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  auto k = pose_clips_kernel<CPL, NB, NBF, SPL>;
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, block, smem, s>>>(t->T, a);
+  CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+template <int CPL, int NB, int NBF, int SPL>
+static int launch_batch(const stacb_tree *t, const BatchArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  auto k = batch_kernel<CPL, NB, NBF, SPL>;
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, block, smem, s>>>(t->T, a);
+  CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+
+static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl) {
+  return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl;
+}
+
+static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
+  CUDA_TRY(cudaSetDevice(t->device));
+  CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(int), s));
+  // few chains: one warp per CTA so every chain gets an SM to itself; many: 4 warps per CTA
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  const int wpb = (a.C <= 2 * sms) ? 1 : 4;
+  const int grid = std::min((a.C + wpb - 1) / wpb, sms * 16);
+  const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
+  if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
+#define X(c, n, f, p) \
+  if (fits(t, c, n, f, p)) return launch_pose<c, n, f, p>(t, a, grid, 32 * wpb, smem, s);
+  STACB_VARIANTS(X)
+#undef X
+  return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
+}
+
+static int run_batch(const stacb_tree *t, const BatchArgs &a, cudaStream_t s) {
+  CUDA_TRY(cudaSetDevice(t->device));
+  if (a.B <= 0) return STACB_OK;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  const int wpb = (a.B <= 2 * sms) ? 1 : 4;
+  const int grid = std::min((a.B + wpb - 1) / wpb, sms * 16);
+  const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
+  if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
+#define X(c, n, f, p) \
+  if (fits(t, c, n, f, p)) return launch_batch<c, n, f, p>(t, a, grid, 32 * wpb, smem, s);
+  STACB_VARIANTS(X)
+#undef X
+  return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
+}
+
+extern "C" int stacb_fk(const stacb_tree *t, const float *qpos, const float *site_pos, float *qpos_out, float *xpos, float *xquat,
+                        float *site_xpos, int B, void *stream) {
+  if (!t || !qpos || !site_pos || B < 0) return fail(STACB_E_INVALID, "stacb_fk: bad argument");
+  BatchArgs a{};
+  a.q = qpos; a.site_pos = site_pos; a.out_a = qpos_out; a.out_b = xpos; a.out_c = xquat; a.out_d = site_xpos; a.B = B; a.mode = 0;
+  return run_batch(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_loss_grad(const stacb_tree *t, const float *q, const float *q0, const float *kp, const uint8_t *q_mask,
+                               const uint8_t *kp_mask, const float *site_pos, float *loss, float *grad, int B, void *stream) {
+  if (!t || !q || !kp || !site_pos || !loss || B < 0) return fail(STACB_E_INVALID, "stacb_loss_grad: bad argument");
+  BatchArgs a{};
+  a.q = q; a.q0 = q0; a.kp = kp; a.q_mask = q_mask; a.kp_mask = kp_mask; a.site_pos = site_pos; a.out_a = loss; a.out_b = grad; a.B = B; a.mode = 1;
+  return run_batch(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_q_opt(const stacb_tree *t, const float *q0, const float *kp, const uint8_t *q_mask, const uint8_t *kp_mask,
+                           const float *site_pos, const float *lb, const float *ub, float tol, int maxiter, int maxls, float *params,
+                           float *error, int32_t *iters, int32_t *ls_evals, int B, void *stream) {
+  if (!t || !q0 || !kp || !site_pos || !lb || !ub || !params || !error || !iters || !ls_evals || B < 0)
+    return fail(STACB_E_INVALID, "stacb_q_opt: bad argument");
+  BatchArgs a{};
+  a.q = q0; a.kp = kp; a.q_mask = q_mask; a.kp_mask = kp_mask; a.site_pos = site_pos; a.lb = lb; a.ub = ub; a.tol = tol; a.maxiter = maxiter;
+  a.maxls = maxls; a.out_a = params; a.out_b = error; a.iters = iters; a.ls_evals = ls_evals; a.B = B; a.mode = 2;
+  return run_batch(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_pose_clips(const stacb_tree *t, const float *kp, float *qpos_io, const float *site_pos, const float *lb, const float *ub,
+                                const uint8_t *part_masks, int P, int do_root, int root_kp_idx, const uint8_t *trunk_kps, int root_dims,
+                                float tol, int maxiter, int maxls, float *qpos, float *xpos, float *xquat, float *sites, float *err,
+                                int32_t *iters, int32_t *ls_evals, int32_t *root_stats, int32_t *status, int C, int F, void *stream) {
+  if (!t || !kp || !qpos_io || !site_pos || !lb || !ub || C < 0 || F < 0 || P < 0) return fail(STACB_E_INVALID, "stacb_pose_clips: bad argument");
+  if (P > 0 && !part_masks) return fail(STACB_E_INVALID, "stacb_pose_clips: part_masks is null");
+  if (do_root && (root_kp_idx < 0 || root_kp_idx >= t->T.K || F < 1)) return fail(STACB_E_INVALID, "stacb_pose_clips: bad root keypoint");
+  if ((iters == nullptr) != (ls_evals == nullptr)) return fail(STACB_E_INVALID, "stacb_pose_clips: iters and ls_evals go together");
+  if (C == 0) return STACB_OK;
+  PoseArgs a{};
+  a.kp = kp; a.qpos_io = qpos_io; a.site_pos = site_pos; a.lb = lb; a.ub = ub; a.part_masks = part_masks; a.P = P; a.do_root = do_root;
+  a.root_kp_idx = root_kp_idx; a.trunk_kps = trunk_kps; a.root_dims = root_dims; a.tol = tol; a.maxiter = maxiter; a.maxls = maxls;
+  a.qpos = qpos; a.xpos = xpos; a.xquat = xquat; a.sites = sites; a.err = err; a.iters = iters; a.ls_evals = ls_evals;
+  a.root_stats = root_stats; a.status = status; a.C = C; a.F = F; a.counter = t->counter;
+  return run_pose(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_m_stats(const stacb_tree *t, const float *kp, const float *q, float *scratch, float *s_out, float *z2, int T,
+                             void *stream) {
+  if (!t || !kp || !q || !scratch || !s_out || !z2 || T < 0) return fail(STACB_E_INVALID, "stacb_m_stats: bad argument");
+  BatchArgs a{};
+  a.q = q; a.kp = kp; a.site_pos = nullptr; a.out_a = scratch; a.B = T; a.mode = 3;
+  int rc = run_batch(t, a, (cudaStream_t)stream);
+  if (rc) return rc;
+  const int n3k = 3 * t->T.K;
+  m_reduce_kernel<<<(n3k + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, T, n3k, s_out, z2);
+  CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+
+extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream) {
+  if (!out || blocks <= 0 || threads <= 0 || iters < 0) return fail(STACB_E_INVALID, "stacb_fma_peak: bad argument");
+  fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters);
+  CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+
+extern "C" const char *stacb_last_error(void) { return g_err.c_str(); }
+extern "C" int stacb_version(void) { return STACB_VERSION; }

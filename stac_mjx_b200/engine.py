@@ -1,0 +1,181 @@
+"""Device-side solver handle: torch supplies device memory and streams, libstacb does the work.
+
+`Engine` owns one `stacb_tree` (the tree descriptor copied to a GPU) and exposes the C ABI of
+include/stacb.h on torch CUDA tensors.  Every method enqueues on the current torch stream and
+returns tensors that live on the device; nothing here synchronises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tree import TreeModel
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, tree: TreeModel, site_bodies, device: int | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.StacbError("no CUDA device: the STAC solver path has no CPU fallback")
+        L = _lib.lib()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.tree = tree
+        self.nq, self.nbody, self.K = tree.nq, tree.nbody, len(site_bodies)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        keep = [
+            i32(tree.body_parent), i32(tree.body_jntadr), i32(tree.body_jntnum), f32(tree.body_pos), f32(tree.body_quat),
+            i32(tree.jnt_type), i32(tree.jnt_qposadr), i32(tree.jnt_bodyid), f32(tree.jnt_pos), f32(tree.jnt_axis),
+            f32(tree.qpos0), i32(site_bodies),
+        ]  # fmt: skip
+        desc = _lib.TreeDesc(tree.nbody, tree.nq, tree.njnt, self.K, *[a.ctypes.data_as(C.c_void_p) for a in keep])
+        h = C.c_void_p()
+        _lib.check(L.stacb_tree_create(C.byref(desc), self.device.index or 0, C.byref(h)), "stacb_tree_create")
+        self._h, self._L = h, L
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.stacb_tree_destroy(h)
+            self._h = None
+
+    # -- helpers ---------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def f32(self, a, shape=None) -> torch.Tensor:
+        t = torch.as_tensor(np.asarray(a, dtype=np.float32) if not isinstance(a, torch.Tensor) else a)
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def u8(self, a, shape=None) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device).to(torch.uint8).contiguous()
+        else:
+            t = torch.as_tensor(np.asarray(a).astype(np.uint8)).to(self.device).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def empty(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    @property
+    def smem_per_chain(self) -> int:
+        return int(self._L.stacb_tree_smem_per_chain(self._h))
+
+    # -- utils.kinematics + get_site_xpos ----------------------------------
+    def fk(self, qpos, site_pos):
+        qpos = self.f32(qpos)
+        B = qpos.shape[0]
+        site_pos = self.f32(site_pos, (self.K, 3))
+        qout, xpos = self.empty(B, self.nq), self.empty(B, self.nbody, 3)
+        xquat, sx = self.empty(B, self.nbody, 4), self.empty(B, self.K, 3)
+        rc = self._L.stacb_fk(self._h, _ptr(qpos), _ptr(site_pos), _ptr(qout), _ptr(xpos), _ptr(xquat), _ptr(sx), B, self._stream())
+        _lib.check(rc, "stacb_fk")
+        return qout, xpos, xquat, sx
+
+    # -- stac_core.q_loss and its gradient ---------------------------------
+    def loss_grad(self, q, q0, kp, q_mask, kp_mask, site_pos, want_grad=True):
+        q, q0, kp = self.f32(q), self.f32(q0), self.f32(kp)
+        B = q.shape[0]
+        q_mask, kp_mask = self.u8(q_mask, (self.nq,)), self.u8(kp_mask, (3 * self.K,))
+        site_pos = self.f32(site_pos, (self.K, 3))
+        loss = self.empty(B)
+        grad = self.empty(B, self.nq) if want_grad else None
+        rc = self._L.stacb_loss_grad(
+            self._h, _ptr(q), _ptr(q0), _ptr(kp), _ptr(q_mask), _ptr(kp_mask), _ptr(site_pos), _ptr(loss), _ptr(grad), B, self._stream()
+        )
+        _lib.check(rc, "stacb_loss_grad")
+        return loss, grad
+
+    # -- stac_core._q_opt ----------------------------------------------------
+    def q_opt(self, q0, kp, q_mask, kp_mask, site_pos, lb, ub, tol, maxiter=400, maxls=15):
+        q0, kp = self.f32(q0), self.f32(kp)
+        B = q0.shape[0]
+        q_mask, kp_mask = self.u8(q_mask, (self.nq,)), self.u8(kp_mask, (3 * self.K,))
+        site_pos, lb, ub = self.f32(site_pos, (self.K, 3)), self.f32(lb, (self.nq,)), self.f32(ub, (self.nq,))
+        params, err = self.empty(B, self.nq), self.empty(B)
+        iters, ls = self.empty(B, dtype=torch.int32), self.empty(B, dtype=torch.int32)
+        rc = self._L.stacb_q_opt(
+            self._h, _ptr(q0), _ptr(kp), _ptr(q_mask), _ptr(kp_mask), _ptr(site_pos), _ptr(lb), _ptr(ub),
+            float(tol), int(maxiter), int(maxls), _ptr(params), _ptr(err), _ptr(iters), _ptr(ls), B, self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "stacb_q_opt")
+        return params, err, iters, ls
+
+    # -- fused root_optimization + pose_optimization over clips -------------
+    def pose_clips(self, kp, qpos_io, site_pos, lb, ub, part_masks, *, do_root, root_kp_idx=-1, trunk_kps=None,
+                   root_dims=7, tol=1e-4, maxiter=400, maxls=15, out=None, want_stats=True):  # fmt: skip
+        """kp [C,F,3K] (device), qpos_io [C,nq] (device, updated in place). Returns dict of device tensors."""
+        kp = self.f32(kp)
+        Cn, F = int(kp.shape[0]), int(kp.shape[1])
+        if kp.shape[2] != 3 * self.K:
+            raise ValueError("kp must be [C, F, 3K]")
+        if not (isinstance(qpos_io, torch.Tensor) and qpos_io.is_cuda and qpos_io.dtype == torch.float32 and qpos_io.is_contiguous()):
+            raise ValueError("qpos_io must be a contiguous float32 CUDA tensor [C, nq] (it is updated in place)")
+        if tuple(qpos_io.shape) != (Cn, self.nq):
+            raise ValueError("qpos_io must be [C, nq]")
+        site_pos, lb, ub = self.f32(site_pos, (self.K, 3)), self.f32(lb, (self.nq,)), self.f32(ub, (self.nq,))
+        pm = self.u8(np.asarray(part_masks).reshape(-1, self.nq)) if not isinstance(part_masks, torch.Tensor) else self.u8(part_masks)
+        P = int(pm.shape[0]) if pm.numel() else 0
+        trunk = self.u8(trunk_kps if trunk_kps is not None else np.ones(self.K), (self.K,))
+        if out is None:
+            out = {}
+        o = lambda k, *shape, dtype=torch.float32: out.setdefault(k, self.empty(*shape, dtype=dtype))
+        qpos, xpos = o("qpos", Cn, F, self.nq), o("xpos", Cn, F, self.nbody, 3)
+        xquat, sites, err = o("xquat", Cn, F, self.nbody, 4), o("sites", Cn, F, self.K, 3), o("err", Cn, F)
+        if want_stats:
+            iters, ls = o("iters", Cn, F, 1 + P, dtype=torch.int32), o("ls_evals", Cn, F, 1 + P, dtype=torch.int32)
+            rs = out.setdefault("root_stats", torch.zeros(Cn, 4, dtype=torch.int32, device=self.device))
+        else:
+            iters = ls = rs = None
+        status = o("status", Cn, dtype=torch.int32)
+        rc = self._L.stacb_pose_clips(
+            self._h, _ptr(kp), _ptr(qpos_io), _ptr(site_pos), _ptr(lb), _ptr(ub), _ptr(pm) if P else None, P,
+            int(bool(do_root)), int(root_kp_idx), _ptr(trunk), int(root_dims), float(tol), int(maxiter), int(maxls),
+            _ptr(qpos), _ptr(xpos), _ptr(xquat), _ptr(sites), _ptr(err), _ptr(iters), _ptr(ls), _ptr(rs), _ptr(status),
+            Cn, F, self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "stacb_pose_clips")
+        return out
+
+    # -- stac_core._m_opt sufficient statistics ------------------------------
+    def m_stats(self, kp, q):
+        kp, q = self.f32(kp), self.f32(q)
+        T = int(kp.shape[0])
+        scratch = self.empty(max(T, 1), 3 * self.K + 1)
+        s, z2 = self.empty(self.K, 3), self.empty(1)
+        rc = self._L.stacb_m_stats(self._h, _ptr(kp), _ptr(q), _ptr(scratch), _ptr(s), _ptr(z2), T, self._stream())
+        _lib.check(rc, "stacb_m_stats")
+        return s, z2
+
+    def fma_peak_tflops(self, iters: int = 20000) -> float:
+        """Measured FP32 FMA throughput (TFLOP/s) of this GPU: bench.py's roofline denominator."""
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        blocks, threads = sms * 8, 256
+        out = self.empty(blocks * threads)
+        s = self._stream()
+        self._L.stacb_fma_peak(_ptr(out), blocks, threads, 200, s)
+        torch.cuda.synchronize(self.device)
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(self._L.stacb_fma_peak(_ptr(out), blocks, threads, iters, s), "stacb_fma_peak")
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            ms = e0.elapsed_time(e1)
+            best = max(best, 2.0 * 16 * iters * blocks * threads / (ms * 1e-3) / 1e12)
+        return best
