@@ -104,7 +104,8 @@ int stacb_q_opt(const stacb_tree *tree, const float *q0, const float *kp, const 
  *   kp [C,F,3K]
  *   qpos_io [C,nq]   in: mjx_data.qpos on entry of each clip;  out: qpos after the last frame
  *   part_masks [P,nq] u8 (INDIVIDUAL_PART_OPTIMIZATION masks, stac.py:161-183), P may be 0
- *   do_root, root_kp_idx, trunk_kps [K] u8, root_dims (7 free / 4 slide; compute_stac.py:51-54)
+ *   do_root: 0 = pose only, 1 = root optimisation on frame 0 then pose, 2 = root optimisation only
+ *   root_kp_idx, trunk_kps [K] u8, root_dims (7 free / 4 slide; compute_stac.py:51-54)
  *   qpos [C,F,nq]  xpos [C,F,nbody,3]  xquat [C,F,nbody,4]  sites [C,F,K,3]  err [C,F]
  *   iters, ls_evals [C,F,1+P]  root_stats [C,4] = {iters,ls} of the two root solves
  *   status [C]: 0 ok, 1 = a non-finite loss was seen in the clip

@@ -108,7 +108,7 @@ class TorchModel:
         qv = tt(q).requires_grad_(True)
         loss = self.q_loss(qv, tt(kp), tt(qmask), tt(kpmask), tt(q0), tt(site_pos))
         (g,) = torch.autograd.grad(loss, qv)
-        return float(loss), g.numpy()
+        return float(loss.detach()), g.numpy()
 
     def projected_gradient(self, q0, lb, ub, qmask, kp, kpmask, site_pos, tol, maxiter=400, maxls=15):
         """jaxopt 0.8.5 ProximalGradient._update_accel / _ls / _error with prox = box clip."""

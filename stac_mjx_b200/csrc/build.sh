@@ -1,9 +1,23 @@
 #!/bin/sh
-# Build libstacb.so (sm_100a) in-tree. -fmad=false: fused multiply-adds are explicit in the source.
+# Build libstacb.so (sm_100a) in-tree; one translation unit per kernel variant, compiled in parallel.
+# -fmad=false: fused multiply-adds are explicit in the source (canonical arithmetic).
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
-  -Xcompiler -fPIC -shared -I ../../include ${STACB_NVCC_EXTRA} \
-  stacb_kernels.cu -o ../libstacb.so
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -I ../../include ${STACB_NVCC_EXTRA}"
+mkdir -p _obj
+VARIANTS=$(sed -n 's/^#define STACB_VARIANTS(X)//p' stacb_variants.h | sed 's/X(\([0-9]*\), *\([0-9]*\), *\([0-9]*\), *\([0-9]*\))/\1_\2_\3_\4/g')
+pids=""
+for v in $VARIANTS; do
+  set -- $(echo $v | tr '_' ' ')
+  $NVCC $FLAGS -DV_CPL=$1 -DV_NB=$2 -DV_NBF=$3 -DV_SPL=$4 -c stacb_variant.cu -o _obj/variant_$v.o > _obj/variant_$v.log 2>&1 &
+  pids="$pids $!"
+done
+$NVCC $FLAGS -c stacb_abi.cu -o _obj/abi.o > _obj/abi.log 2>&1 &
+pids="$pids $!"
+rc=0
+for p in $pids; do wait $p || rc=1; done
+cat _obj/*.log
+[ $rc -eq 0 ] || { echo "stacb build failed"; exit 1; }
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libstacb.so _obj/*.o
 echo "built $(cd .. && pwd)/libstacb.so"

@@ -1,0 +1,304 @@
+// stacb_abi.cu -- host side of libstacb.so: schedule derivation, variant dispatch, C ABI (include/stacb.h).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "stacb.h"
+#include "stacb_device.cuh"
+#include "stacb_variants.h"
+
+namespace stacb {
+
+// Sequential (index-order) reduction of the per-frame m-phase contributions: one thread per output.
+__global__ void m_reduce_kernel(const float *__restrict__ contrib, int T, int n3k, float *__restrict__ s, float *__restrict__ z2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n3k) return;
+  float acc = 0.f;
+  for (int t = 0; t < T; t++) acc = acc + contrib[(size_t)t * (n3k + 1) + c];
+  if (c < n3k) s[c] = acc; else z2[0] = acc;
+}
+
+__global__ void fma_peak_kernel(float *out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+  const float m = 0.9999f, c = 1e-4f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+
+}  // namespace stacb
+
+// ------------------------------------------------------------------------------------------
+// host side: schedule derivation + C ABI
+// ------------------------------------------------------------------------------------------
+
+using namespace stacb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(STACB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct stacb_tree {
+  int device;
+  DevTree T;
+  int cpl, bpl_act, bpl_full;
+  std::vector<void *> allocs;
+  int *counter;
+};
+
+static int ceil_log2(int x) { int r = 0; while ((1 << r) < x) r++; return r; }
+
+template <class V>
+static int upload(stacb_tree *t, const std::vector<V> &h, const V **out) {
+  void *d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(V);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  t->allocs.push_back(d);
+  if (!h.empty()) CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+  *out = (const V *)d;
+  return STACB_OK;
+}
+
+static int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+
+// Body-set records (parents precede children because body ids are DFS pre-order).
+static void build_set(const stacb_tree_desc &m, const std::vector<int> &set, const std::vector<int> &subsize, const std::vector<int> &order,
+                      std::vector<int> &rec, std::vector<int> &anc, int &rounds) {
+  const int n = (int)set.size();
+  std::vector<int> loc(m.nbody, -1), depth(m.nbody, 0);
+  for (int b = 1; b < m.nbody; b++) depth[b] = depth[m.body_parent[b]] + 1;
+  int maxd = 1;
+  for (int e = 0; e < n; e++) { loc[set[e]] = e; maxd = std::max(maxd, depth[set[e]]); }
+  rounds = ceil_log2(maxd);
+  rec.assign((size_t)n * REC, 0);
+  for (int e = 0; e < n; e++) {
+    const int b = set[e];
+    int *r = rec.data() + (size_t)e * REC;
+    for (int c = 0; c < 3; c++) r[R_POS + c] = f2i(m.body_pos[3 * b + c]);
+    for (int c = 0; c < 4; c++) r[R_QUAT + c] = f2i(m.body_quat[4 * b + c]);
+    r[R_NJNT] = m.body_jntnum[b];
+    const int p = m.body_parent[b];
+    r[R_PARENT] = (p != 0) ? loc[p] : -1;
+    r[R_BODY] = b;
+    for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
+      const int j = m.body_jntadr[b] + jj;
+      int *jr = r + R_JNT + J_STRIDE * jj;
+      jr[J_TYPE] = m.jnt_type[j];
+      jr[J_ADR] = m.jnt_qposadr[j];
+      for (int c = 0; c < 3; c++) { jr[J_POS + c] = f2i(m.jnt_pos[3 * j + c]); jr[J_AXIS + c] = f2i(m.jnt_axis[3 * j + c]); }
+      const int t = m.jnt_type[j];
+      jr[J_REF] = f2i((t == STACB_JNT_HINGE || t == STACB_JNT_SLIDE) ? m.qpos0[m.jnt_qposadr[j]] : 0.f);
+      // sorted-site range under this body
+      const int lo = b, hi = b + subsize[b], K = m.nsite;
+      int a = 0;
+      while (a < K && m.site_body[order[a]] < lo) a++;
+      int e2 = a;
+      while (e2 < K && m.site_body[order[e2]] < hi) e2++;
+      jr[J_SA] = a;
+      jr[J_SE] = e2;
+    }
+  }
+  const int nr = std::max(rounds, 1);
+  anc.assign((size_t)nr * n, -1);
+  for (int e = 0; e < n; e++) anc[e] = rec[(size_t)e * REC + R_PARENT];
+  for (int r = 1; r < nr; r++)
+    for (int e = 0; e < n; e++) {
+      const int a = anc[(size_t)(r - 1) * n + e];
+      anc[(size_t)r * n + e] = (a >= 0) ? anc[(size_t)(r - 1) * n + a] : -1;
+    }
+}
+
+extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tree **out) {
+  if (!d || !out) return fail(STACB_E_INVALID, "null argument");
+  const stacb_tree_desc &m = *d;
+  if (m.nbody < 2 || m.nq < 1 || m.njnt < 0 || m.nsite < 1) return fail(STACB_E_INVALID, "empty model");
+  for (int b = 1; b < m.nbody; b++) {
+    if (m.body_parent[b] < 0 || m.body_parent[b] >= b) return fail(STACB_E_INVALID, "body ids must be in depth-first pre-order");
+    if (m.body_jntnum[b] > JMAX) return fail(STACB_E_UNSUPPORTED, "more than 3 joints on one body");
+    for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
+      const int j = m.body_jntadr[b] + jj, t = m.jnt_type[j];
+      if (t == STACB_JNT_FREE && (m.body_parent[b] != 0 || m.body_jntnum[b] != 1))
+        return fail(STACB_E_INVALID, "a free joint must be the only joint of a top-level body");
+      if (t == STACB_JNT_BALL && jj != m.body_jntnum[b] - 1) return fail(STACB_E_UNSUPPORTED, "a ball joint must be the last joint of its body");
+      if (t < 0 || t > 3) return fail(STACB_E_INVALID, "unknown joint type");
+    }
+  }
+  for (int k = 0; k < m.nsite; k++)
+    if (m.site_body[k] <= 0 || m.site_body[k] >= m.nbody) return fail(STACB_E_INVALID, "keypoint site must be attached to a non-world body");
+  CUDA_TRY(cudaSetDevice(device));
+  stacb_tree *t = new stacb_tree();
+  t->device = device;
+  const int nb = m.nbody, K = m.nsite;
+  std::vector<int> subsize(nb, 0);
+  for (int b = nb - 1; b >= 0; b--) { subsize[b] += 1; if (b > 0) subsize[m.body_parent[b]] += subsize[b]; }
+  std::vector<char> isact(nb, 0);
+  for (int k = 0; k < K; k++) { int b = m.site_body[k]; while (b != 0 && !isact[b]) { isact[b] = 1; b = m.body_parent[b]; } }
+  std::vector<int> act, full;
+  for (int b = 1; b < nb; b++) { full.push_back(b); if (isact[b]) act.push_back(b); }
+  std::vector<int> order(K);
+  for (int k = 0; k < K; k++) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m.site_body[a] < m.site_body[b]; });
+  std::vector<int> rec_a, anc_a, rec_f, anc_f;
+  int ra, rf;
+  build_set(m, act, subsize, order, rec_a, anc_a, ra);
+  build_set(m, full, subsize, order, rec_f, anc_f, rf);
+  std::vector<int> loc_a(nb, -1), loc_f(nb, -1), se_a(K), se_f(K);
+  for (size_t e = 0; e < act.size(); e++) loc_a[act[e]] = (int)e;
+  for (size_t e = 0; e < full.size(); e++) loc_f[full[e]] = (int)e;
+  for (int p = 0; p < K; p++) { se_a[p] = loc_a[m.site_body[order[p]]]; se_f[p] = loc_f[m.site_body[order[p]]]; }
+  DevTree &T = t->T;
+  T.nbody = nb; T.nq = m.nq; T.njnt = m.njnt; T.K = K; T.spl = std::max(1, (K + 31) / 32);
+  T.act.n = (int)act.size(); T.act.rounds = ra;
+  T.full.n = (int)full.size(); T.full.rounds = rf;
+  int rc;
+  if ((rc = upload(t, rec_a, &T.act.rec)) || (rc = upload(t, anc_a, &T.act.anc)) || (rc = upload(t, rec_f, &T.full.rec)) ||
+      (rc = upload(t, anc_f, &T.full.anc)) || (rc = upload(t, order, &T.site_order)) || (rc = upload(t, se_a, &T.site_eact)) ||
+      (rc = upload(t, se_f, &T.site_efull))) {
+    stacb_tree_destroy(t);
+    return rc;
+  }
+  t->cpl = (m.nq + 31) / 32; t->bpl_act = (T.act.n + 31) / 32; t->bpl_full = (T.full.n + 31) / 32;
+  T.nqp = 32 * t->cpl; T.pqn = std::max(T.act.n, T.full.n); T.npre = 32 * T.spl;
+  void *cnt = nullptr;
+  if (cudaMalloc(&cnt, sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
+  t->allocs.push_back(cnt);
+  t->counter = (int *)cnt;
+  *out = t;
+  return STACB_OK;
+}
+
+extern "C" void stacb_tree_destroy(stacb_tree *t) {
+  if (!t) return;
+  for (void *p : t->allocs) cudaFree(p);
+  delete t;
+}
+
+extern "C" int stacb_tree_smem_per_chain(const stacb_tree *t) { return t ? chain_smem_floats(t->T) * 4 : 0; }
+
+namespace stacb {
+#define X(c, n, f, p)                                                                                                   \
+  cudaError_t launch_pose_##c##_##n##_##f##_##p(const DevTree &, const PoseArgs &, int, int, size_t, cudaStream_t);     \
+  cudaError_t launch_batch_##c##_##n##_##f##_##p(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t);
+STACB_VARIANTS(X)
+#undef X
+}  // namespace stacb
+
+static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl) {
+  return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl;
+}
+
+static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
+  CUDA_TRY(cudaSetDevice(t->device));
+  CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(int), s));
+  // few chains: one warp per CTA so every chain gets an SM to itself; many: 4 warps per CTA
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  const int wpb = (a.C <= 2 * sms) ? 1 : 4;
+  const int grid = std::min((a.C + wpb - 1) / wpb, sms * 16);
+  const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
+  if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
+#define X(c, n, f, p) \
+  if (fits(t, c, n, f, p)) { CUDA_TRY(launch_pose_##c##_##n##_##f##_##p(t->T, a, grid, 32 * wpb, smem, s)); return STACB_OK; }
+  STACB_VARIANTS(X)
+#undef X
+  return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
+}
+
+static int run_batch(const stacb_tree *t, const BatchArgs &a, cudaStream_t s) {
+  CUDA_TRY(cudaSetDevice(t->device));
+  if (a.B <= 0) return STACB_OK;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  const int wpb = (a.B <= 2 * sms) ? 1 : 4;
+  const int grid = std::min((a.B + wpb - 1) / wpb, sms * 16);
+  const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
+  if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
+#define X(c, n, f, p) \
+  if (fits(t, c, n, f, p)) { CUDA_TRY(launch_batch_##c##_##n##_##f##_##p(t->T, a, grid, 32 * wpb, smem, s)); return STACB_OK; }
+  STACB_VARIANTS(X)
+#undef X
+  return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
+}
+
+extern "C" int stacb_fk(const stacb_tree *t, const float *qpos, const float *site_pos, float *qpos_out, float *xpos, float *xquat,
+                        float *site_xpos, int B, void *stream) {
+  if (!t || !qpos || !site_pos || B < 0) return fail(STACB_E_INVALID, "stacb_fk: bad argument");
+  BatchArgs a{};
+  a.q = qpos; a.site_pos = site_pos; a.out_a = qpos_out; a.out_b = xpos; a.out_c = xquat; a.out_d = site_xpos; a.B = B; a.mode = 0;
+  return run_batch(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_loss_grad(const stacb_tree *t, const float *q, const float *q0, const float *kp, const uint8_t *q_mask,
+                               const uint8_t *kp_mask, const float *site_pos, float *loss, float *grad, int B, void *stream) {
+  if (!t || !q || !kp || !site_pos || !loss || B < 0) return fail(STACB_E_INVALID, "stacb_loss_grad: bad argument");
+  BatchArgs a{};
+  a.q = q; a.q0 = q0; a.kp = kp; a.q_mask = q_mask; a.kp_mask = kp_mask; a.site_pos = site_pos; a.out_a = loss; a.out_b = grad; a.B = B; a.mode = 1;
+  return run_batch(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_q_opt(const stacb_tree *t, const float *q0, const float *kp, const uint8_t *q_mask, const uint8_t *kp_mask,
+                           const float *site_pos, const float *lb, const float *ub, float tol, int maxiter, int maxls, float *params,
+                           float *error, int32_t *iters, int32_t *ls_evals, int B, void *stream) {
+  if (!t || !q0 || !kp || !site_pos || !lb || !ub || !params || !error || !iters || !ls_evals || B < 0)
+    return fail(STACB_E_INVALID, "stacb_q_opt: bad argument");
+  BatchArgs a{};
+  a.q = q0; a.kp = kp; a.q_mask = q_mask; a.kp_mask = kp_mask; a.site_pos = site_pos; a.lb = lb; a.ub = ub; a.tol = tol; a.maxiter = maxiter;
+  a.maxls = maxls; a.out_a = params; a.out_b = error; a.iters = iters; a.ls_evals = ls_evals; a.B = B; a.mode = 2;
+  return run_batch(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_pose_clips(const stacb_tree *t, const float *kp, float *qpos_io, const float *site_pos, const float *lb, const float *ub,
+                                const uint8_t *part_masks, int P, int do_root, int root_kp_idx, const uint8_t *trunk_kps, int root_dims,
+                                float tol, int maxiter, int maxls, float *qpos, float *xpos, float *xquat, float *sites, float *err,
+                                int32_t *iters, int32_t *ls_evals, int32_t *root_stats, int32_t *status, int C, int F, void *stream) {
+  if (!t || !kp || !qpos_io || !site_pos || !lb || !ub || C < 0 || F < 0 || P < 0) return fail(STACB_E_INVALID, "stacb_pose_clips: bad argument");
+  if (P > 0 && !part_masks) return fail(STACB_E_INVALID, "stacb_pose_clips: part_masks is null");
+  if (do_root && (root_kp_idx < 0 || root_kp_idx >= t->T.K || F < 1)) return fail(STACB_E_INVALID, "stacb_pose_clips: bad root keypoint");
+  if ((iters == nullptr) != (ls_evals == nullptr)) return fail(STACB_E_INVALID, "stacb_pose_clips: iters and ls_evals go together");
+  if (C == 0) return STACB_OK;
+  PoseArgs a{};
+  a.kp = kp; a.qpos_io = qpos_io; a.site_pos = site_pos; a.lb = lb; a.ub = ub; a.part_masks = part_masks; a.P = P; a.do_root = do_root;
+  a.root_kp_idx = root_kp_idx; a.trunk_kps = trunk_kps; a.root_dims = root_dims; a.tol = tol; a.maxiter = maxiter; a.maxls = maxls;
+  a.qpos = qpos; a.xpos = xpos; a.xquat = xquat; a.sites = sites; a.err = err; a.iters = iters; a.ls_evals = ls_evals;
+  a.root_stats = root_stats; a.status = status; a.C = C; a.F = F; a.counter = t->counter;
+  return run_pose(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_m_stats(const stacb_tree *t, const float *kp, const float *q, float *scratch, float *s_out, float *z2, int T,
+                             void *stream) {
+  if (!t || !kp || !q || !scratch || !s_out || !z2 || T < 0) return fail(STACB_E_INVALID, "stacb_m_stats: bad argument");
+  BatchArgs a{};
+  a.q = q; a.kp = kp; a.site_pos = nullptr; a.out_a = scratch; a.B = T; a.mode = 3;
+  int rc = run_batch(t, a, (cudaStream_t)stream);
+  if (rc) return rc;
+  const int n3k = 3 * t->T.K;
+  m_reduce_kernel<<<(n3k + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, T, n3k, s_out, z2);
+  CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+
+extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream) {
+  if (!out || blocks <= 0 || threads <= 0 || iters < 0) return fail(STACB_E_INVALID, "stacb_fma_peak: bad argument");
+  fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters);
+  CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+
+extern "C" const char *stacb_last_error(void) { return g_err.c_str(); }
+extern "C" int stacb_version(void) { return STACB_VERSION; }

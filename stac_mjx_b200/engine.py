@@ -142,9 +142,11 @@ class Engine:
         else:
             iters = ls = rs = None
         status = o("status", Cn, dtype=torch.int32)
+        if Cn == 0 or F == 0:
+            return out
         rc = self._L.stacb_pose_clips(
             self._h, _ptr(kp), _ptr(qpos_io), _ptr(site_pos), _ptr(lb), _ptr(ub), _ptr(pm) if P else None, P,
-            int(bool(do_root)), int(root_kp_idx), _ptr(trunk), int(root_dims), float(tol), int(maxiter), int(maxls),
+            int(do_root), int(root_kp_idx), _ptr(trunk), int(root_dims), float(tol), int(maxiter), int(maxls),
             _ptr(qpos), _ptr(xpos), _ptr(xquat), _ptr(sites), _ptr(err), _ptr(iters), _ptr(ls), _ptr(rs), _ptr(status),
             Cn, F, self._stream(),
         )  # fmt: skip

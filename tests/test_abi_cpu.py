@@ -1,0 +1,65 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/stacb.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_symbols():
+    text = (ROOT / "include" / "stacb.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(stacb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    from stac_mjx_b200 import _lib
+
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    from stac_mjx_b200 import _lib
+
+    if not _lib.LIB_PATH.exists():
+        pytest.fail("stac_mjx_b200/libstacb.so is not built; run `python __graft_entry__.py`")
+    L = ctypes.CDLL(str(_lib.LIB_PATH))
+    for sym in header_symbols():
+        assert hasattr(L, sym), f"{sym} missing from libstacb.so"
+    L.stacb_version.restype = ctypes.c_int
+    m = re.search(r"#define STACB_VERSION (\d+)", (ROOT / "include" / "stacb.h").read_text())
+    assert L.stacb_version() == int(m.group(1))
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    from stac_mjx_b200 import _lib
+
+    L = _lib.lib()
+    assert L.stacb_fk(None, None, None, None, None, None, None, 1, None) == -1
+    assert b"stacb_fk" in L.stacb_last_error()
+    assert L.stacb_tree_create(None, 0, None) == -1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "stac_mjx_b200"
+    for p in pkg.rglob("*.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M), p
+        assert "oracle/" not in p.read_text(), p
+    for p in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.sh")) + [ROOT / "include" / "stacb.h"]:
+        assert not re.search(r"#include.*oracle|oracle/", p.read_text()), p
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+
+    from conftest import get_case
+    from stac_mjx_b200 import _lib
+    from stac_mjx_b200.engine import Engine
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    c = get_case("synth_data")
+    with pytest.raises(_lib.StacbError):
+        Engine(c.tree, c.setup.site_bodies)

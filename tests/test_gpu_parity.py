@@ -1,0 +1,249 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors.
+
+Tolerances are the ones BASELINE.json's north_star states: final qpos within 1e-3 rad, per-marker
+position within 1e-4 m, per-frame loss / solver error within 1e-3 relative.  The kernels are written to
+reproduce the oracle's canonical float32 arithmetic, so in practice the differences are zero; the tests
+assert the stated tolerances and additionally report whether the match was bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, get_case
+
+pytestmark = pytest.mark.gpu
+
+QPOS_TOL, MARKER_TOL, REL_TOL = 1e-3, 1e-4, 1e-3
+MODELS = ["rodent", "celegans", "fly_treadmill", "synth_data", "mouse"]
+
+
+def golden(name):
+    return np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_fk_matches_golden(name, engine_of):
+    c, g = get_case(name), golden(name)
+    eng = engine_of(c)
+    qo, xp, xq, sx = [npy(t) for t in eng.fk(g["q"], g["offsets"])]
+    np.testing.assert_allclose(xp, g["c32_fk_xpos"], atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(sx, g["c32_fk_sites"], atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(xq, g["c32_fk_xquat"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(qo, g["c32_fk_qpos"], atol=1e-6, rtol=0)
+    # and against the float64 MJX-order values (the mathematics, not the rounding)
+    np.testing.assert_allclose(xp, g["f64_fk_xpos"], atol=5e-6 * max(1.0, np.abs(g["f64_fk_xpos"]).max()))
+    assert np.array_equal(xp, g["c32_fk_xpos"]) and np.array_equal(xq, g["c32_fk_xquat"]), "FK no longer bit-identical to the canonical oracle"
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_loss_and_gradient_match_golden(name, engine_of):
+    c, g = get_case(name), golden(name)
+    eng = engine_of(c)
+    qm, km = np.ones(c.tree.nq, bool), np.ones(3 * c.K, bool)
+    L, G = [npy(t) for t in eng.loss_grad(g["q"], g["q"], g["kp"][: len(g["q"])], qm, km, g["offsets"])]
+    np.testing.assert_allclose(L, g["c32_loss"], rtol=REL_TOL)
+    np.testing.assert_allclose(G, g["c32_grad"], atol=1e-5 * max(1.0, np.abs(g["c32_grad"]).max()))
+    np.testing.assert_allclose(G, g["f64_grad"], atol=1e-4 * max(1.0, np.abs(g["f64_grad"]).max()))
+    L2, G2 = [npy(t) for t in eng.loss_grad(g["q"], g["q0"], g["kp"][: len(g["q"])], g["qm_part"], g["km_trunk"], g["offsets"])]
+    np.testing.assert_allclose(L2, g["c32_mloss"], rtol=REL_TOL)
+    np.testing.assert_allclose(G2, g["c32_mgrad"], atol=1e-5 * max(1.0, np.abs(g["c32_mgrad"]).max()))
+    assert (G2[:, ~g["qm_part"].astype(bool)] == 0).all()  # masked-out coordinates have zero gradient
+    assert np.array_equal(G, g["c32_grad"]) and np.array_equal(L2, g["c32_mloss"]), "loss/grad no longer bit-identical"
+    Lonly, none = eng.loss_grad(g["q"], g["q"], g["kp"][: len(g["q"])], qm, km, g["offsets"], want_grad=False)
+    assert none is None and np.array_equal(npy(Lonly), L)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_single_solves_match_golden(name, engine_of):
+    c, g = get_case(name), golden(name)
+    eng = engine_of(c)
+    n = len(g["c32_sol_iters"])
+    p, e, it, ls = [npy(t) for t in eng.q_opt(g["q0"][:n], g["kp"][:n], g["root_mask"], g["km_trunk"], g["offsets"], c.setup.lb, c.setup.ub,
+                                               float(g["tol"]), maxiter=50)]  # fmt: skip
+    np.testing.assert_array_equal(it, g["c32_sol_iters"])
+    np.testing.assert_array_equal(ls, g["c32_sol_ls"])
+    np.testing.assert_allclose(p, g["c32_sol_params"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(e, g["c32_sol_err"], rtol=REL_TOL)
+    assert np.array_equal(p, g["c32_sol_params"])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_clips_match_golden(name, engine_of):
+    """root_optimization + pose_optimization over clips, committed oracle output (2 clips x 4 frames)."""
+    c, g = get_case(name), golden(name)
+    eng = engine_of(c)
+    C, F = g["c32_clip_qpos"].shape[:2]
+    qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (C, 1)), device=eng.device)
+    out = eng.pose_clips(g["kp"].reshape(C, F, -1), qio, g["offsets"], c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
+    o = {k: npy(v) for k, v in out.items()}
+    assert (o["status"] == 0).all()
+    np.testing.assert_array_equal(o["iters"], g["c32_clip_iters"])
+    np.testing.assert_array_equal(o["ls_evals"], g["c32_clip_ls_evals"])
+    np.testing.assert_allclose(o["qpos"], g["c32_clip_qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(o["sites"], g["c32_clip_sites"], atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(o["xpos"], g["c32_clip_xpos"], atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(o["err"], g["c32_clip_err"], rtol=REL_TOL)
+    np.testing.assert_array_equal(npy(qio), g["c32_clip_qpos"][:, -1])  # qpos_io carries the last frame's pose
+    for k in ("qpos", "xpos", "xquat", "sites", "err"):
+        assert np.array_equal(o[k], g[f"c32_clip_{k}"]), f"{k} no longer bit-identical to the canonical oracle"
+
+
+def test_rodent_clip_against_live_oracle(rodent, engine_of):
+    """Fresh seeded inputs (not the committed ones): 3 clips x 12 frames of the rodent, all 6 solves per frame."""
+    eng = engine_of(rodent)
+    s = rodent.setup
+    kp, _, _ = rodent.session(36, 12, seed=123)
+    kp = kp.reshape(3, 12, -1)
+    qio = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (3, 1)), device=eng.device)
+    out = eng.pose_clips(kp, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+    ref = rodent.oracle(np.float32, 1).pose_clips(kp, rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=4, **rodent.root_kw())
+    np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
+    np.testing.assert_array_equal(npy(out["root_stats"]), ref["root_stats"])
+    np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(npy(out["sites"]), ref["sites"], atol=MARKER_TOL, rtol=0)
+    # per-frame loss at the solution, recomputed by the oracle from the GPU's qpos
+    res_gpu = ((npy(out["sites"]) - kp.reshape(3, 12, -1, 3)) ** 2).sum((-1, -2))
+    res_ref = ((ref["sites"] - kp.reshape(3, 12, -1, 3)) ** 2).sum((-1, -2))
+    np.testing.assert_allclose(res_gpu, res_ref, rtol=REL_TOL)
+
+
+def test_pose_without_root_and_warm_start_chain(rodent, engine_of):
+    """fit_offsets-style use: do_root=0, second pass warm-started from qpos_io of the first."""
+    eng = engine_of(rodent)
+    s, o = rodent.setup, rodent.oracle(np.float32, 1)
+    kp, _, _ = rodent.session(5, 5, seed=9)
+    kp = kp.reshape(1, 5, -1)
+    qio = torch.tensor(rodent.tree.qpos0.astype(np.float32)[None], device=eng.device)
+    kw = dict(do_root=0, tol=rodent.tol)
+    a = eng.pose_clips(kp, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)
+    a_q = npy(a["qpos"]).copy()
+    b = eng.pose_clips(kp, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)  # continues from pass 1
+    r1 = o.pose_clips(kp, rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)
+    r2 = o.pose_clips(kp, r1["qpos"][:, -1], s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)
+    np.testing.assert_allclose(a_q, r1["qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(npy(b["qpos"]), r2["qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_array_equal(npy(b["iters"]), r2["iters"])
+
+
+def test_edge_cases(rodent, engine_of):
+    eng = engine_of(rodent)
+    s = rodent.setup
+    kp, _, _ = rodent.session(4, 1, seed=2)
+    # F = 1 clips, P = 0 (no part solves), root only (do_root=2)
+    qio = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (4, 1)), device=eng.device)
+    out = eng.pose_clips(kp.reshape(4, 1, -1), qio, s.initial_offsets, s.lb, s.ub, np.zeros((0, rodent.tree.nq), bool), **rodent.root_kw())
+    ref = rodent.oracle(np.float32, 1).pose_clips(kp.reshape(4, 1, -1), rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, [], **rodent.root_kw())
+    assert out["iters"].shape == (4, 1, 1)
+    np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
+    q2 = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (4, 1)), device=eng.device)
+    eng.pose_clips(kp.reshape(4, 1, -1), q2, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **{**rodent.root_kw(), "do_root": 2})
+    assert not torch.equal(q2[:, :7], torch.tensor(rodent.tree.qpos0[:7].astype(np.float32), device=eng.device).expand(4, 7))
+    assert torch.equal(q2[:, 7:], torch.zeros_like(q2[:, 7:]))  # only the root DOFs moved
+    # C = 0 is a no-op; bad shapes raise
+    empty = eng.pose_clips(np.zeros((0, 3, 3 * rodent.K), np.float32), torch.zeros(0, rodent.tree.nq, device=eng.device), s.initial_offsets,
+                           s.lb, s.ub, s.indiv_parts, do_root=0)  # fmt: skip
+    assert empty["qpos"].shape[0] == 0
+    with pytest.raises(ValueError):
+        eng.pose_clips(np.zeros((1, 3, 5), np.float32), qio[:1], s.initial_offsets, s.lb, s.ub, s.indiv_parts, do_root=0)
+    # maxiter = 1: exactly one FISTA iteration per solve
+    one = eng.pose_clips(kp.reshape(4, 1, -1), qio.clone(), s.initial_offsets, s.lb, s.ub, s.indiv_parts, do_root=0, maxiter=1)
+    assert (npy(one["iters"]) == 1).all()
+    # non-finite keypoints poison the loss (reference has no NaN guard) and are flagged
+    bad = kp.reshape(4, 1, -1).copy()
+    bad[2, 0, 5] = np.nan
+    st = eng.pose_clips(bad, qio.clone(), s.initial_offsets, s.lb, s.ub, s.indiv_parts, do_root=0, maxiter=3)["status"]
+    assert npy(st).tolist() == [0, 0, 1, 0]
+
+
+def test_kat_m_opt_on_gpu():
+    """The known-answer tests of reference tests/unit/test_m_opt.py:72-225 through StacCore.m_opt on the GPU."""
+    from test_oracle_cpu import GT_A, GT_B, chain_tree
+    from stac_mjx_b200 import stac_core
+    from stac_mjx_b200.engine import Engine
+
+    t = chain_tree()
+    eng = Engine(t, t.site_bodyid, 0)
+    core = stac_core.StacCore()
+    Z, ONE = np.zeros((3, 3), np.float32), np.ones((3, 3), np.float32)
+
+    def gen(q, off):
+        return eng.fk(q, off)[3].reshape(len(q), -1)
+
+    def m_opt(kp, q, m0, reg_mask, coef):
+        mdl = stac_core.StacModel(engine=eng, site_pos=eng.f32(m0))
+        r = core.m_opt(mdl, None, kp, q, m0, reg_mask, coef, None)
+        return npy(r.params), float(r.error)
+
+    q = np.zeros((5, 3), np.float32)
+    p, err = m_opt(gen(q, GT_A), q, Z, Z, 0.0)
+    np.testing.assert_allclose(p, GT_A, atol=1e-5)
+    assert err < 2e-6  # reference: < 1e-8 in its summation order; one float32 ulp of z2 ~ 7 here
+    q = np.random.RandomState(42).randn(10, 3).astype(np.float32) * 0.5
+    np.testing.assert_allclose(m_opt(gen(q, GT_A), q, Z, Z, 0.0)[0], GT_A, atol=1e-5)
+    q = np.zeros((8, 3), np.float32)
+    q[:, 0] = np.linspace(0.0, np.pi / 4, 8)
+    np.testing.assert_allclose(m_opt(gen(q, GT_B), q, GT_B, Z, 0.0)[0], GT_B, atol=1e-5)
+    q = np.random.RandomState(99).randn(15, 3).astype(np.float32) * 1.5
+    np.testing.assert_allclose(m_opt(gen(q, GT_B), q, Z, Z, 0.0)[0], GT_B, atol=1e-4)
+    q = np.random.RandomState(42).randn(10, 3).astype(np.float32) * 0.3
+    kp = gen(q, GT_A)
+    np.testing.assert_allclose(m_opt(kp, q, ONE * 99.0, ONE, 0.0)[0], GT_A, atol=1e-5)
+    np.testing.assert_allclose(m_opt(kp, q, Z, ONE, 1e6)[0], Z, atol=1e-3)
+    q = np.zeros((10, 3), np.float32)
+    gt = np.full((3, 3), 0.5, np.float32)
+    is_reg = Z.copy()
+    is_reg[0] = 1.0
+    strong, noreg = m_opt(gen(q, gt), q, Z, is_reg, 1e4)[0], m_opt(gen(q, gt), q, Z, is_reg, 0.0)[0]
+    assert np.linalg.norm(strong[0]) < np.linalg.norm(noreg[0])
+    np.testing.assert_allclose(strong[1:], gt[1:], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["rodent", "mouse"])
+def test_m_stats_match_oracle(name, engine_of):
+    c, g = get_case(name), golden(name)
+    eng = engine_of(c)
+    q = g["c32_clip_qpos"].reshape(-1, c.tree.nq)
+    s, z2 = eng.m_stats(g["kp"][: len(q)], q)
+    np.testing.assert_allclose(npy(s), g["c32_m_s"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(npy(z2)[0], g["c32_m_z2"], rtol=1e-5)
+    np.testing.assert_allclose(npy(s), g["f64_m_s"], rtol=0, atol=5e-3 * np.abs(g["f64_m_s"]).max())  # f64 run has its own qpos
+    assert np.array_equal(npy(s), g["c32_m_s"])
+
+
+def test_full_size_properties(rodent, engine_of):
+    """BASELINE config 2 shape (72 clips x 250 frames): size-independent properties + determinism."""
+    eng = engine_of(rodent)
+    s = rodent.setup
+    C, F = 72, 250
+    kp, _, _ = rodent.session(C * F, F, seed=20260101)
+    kpd = torch.tensor(kp.reshape(C, F, -1), device=eng.device)
+    q0 = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (C, 1)), device=eng.device)
+    runs = []
+    for _ in range(2):
+        qio = q0.clone()
+        out = eng.pose_clips(kpd, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+        runs.append({k: npy(v) for k, v in out.items()})
+    a, b = runs
+    for k in a:
+        assert np.array_equal(a[k], b[k]), f"{k} differs between two identical launches"
+    assert (a["status"] == 0).all() and np.isfinite(a["qpos"]).all()
+    np.testing.assert_allclose(np.linalg.norm(a["qpos"][..., 3:7], axis=-1), 1.0, atol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(a["xquat"], axis=-1), 1.0, atol=1e-4)
+    lb, ub = s.lb[7:], s.ub[7:]
+    assert (a["qpos"][..., 7:] >= lb).all() and (a["qpos"][..., 7:] <= ub).all()  # box constraints hold exactly
+    assert (a["iters"] >= 1).all() and (a["iters"] <= 400).all() and (a["ls_evals"] >= a["iters"]).all()
+    resid = np.linalg.norm(a["sites"] - kp.reshape(C, F, -1, 3), axis=-1)
+    assert resid.mean() < 4e-3  # 1 mm observation noise + 2 mm offset perturbation in the synthetic session
+    conv = a["iters"][..., -1] < 400
+    assert (a["err"][conv] <= rodent.tol).all()
+    # oracle spot check on one full-length clip at full size
+    ci = 17
+    ref = rodent.oracle(np.float32, 1).pose_clips(kp.reshape(C, F, -1)[ci : ci + 1], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub,
+                                                  s.indiv_parts, **rodent.root_kw())  # fmt: skip
+    np.testing.assert_allclose(a["qpos"][ci], ref["qpos"][0], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(a["sites"][ci], ref["sites"][0], atol=MARKER_TOL, rtol=0)
+    np.testing.assert_array_equal(a["iters"][ci], ref["iters"][0])

@@ -1,0 +1,178 @@
+"""Host-side logic that needs no GPU: clip batching, the duck-typed solver seam, packaging layout, pipeline errors.
+
+Mirrors reference tests/unit/test_utils_math.py:41-50, tests/unit/test_compute_stac.py:54-182,
+tests/unit/test_stac_package.py and tests/unit/test_main_run_stac.py.
+"""
+import types
+
+import numpy as np
+import pytest
+
+from stac_mjx_b200 import compute_stac, config, io, main, parallel, utils
+
+
+def test_batch_kp_data_shapes():
+    assert utils.batch_kp_data(np.zeros((10, 6), np.float32), 4).shape == (2, 4, 6)
+    assert utils.batch_kp_data(np.zeros((30, 6), np.float32), 10, continuous=True).shape == (3, 20, 6)
+
+
+def test_batch_kp_data_continuous_overlap_and_wrap():
+    kp = np.arange(30, dtype=np.float32).reshape(30, 1).repeat(3, 1)
+    b = utils.batch_kp_data(kp, 10, continuous=True)
+    np.testing.assert_array_equal(b[0, :, 0], np.arange(20))
+    np.testing.assert_array_equal(b[1, :, 0], np.arange(10, 30))
+    np.testing.assert_array_equal(b[2, :, 0], np.r_[np.arange(20, 30), np.arange(20, 30)])  # mode="wrap" pad of the last clip
+
+
+class FakeData:
+    def __init__(self, qpos, site_xpos=None, xpos=None, xquat=None):
+        self.qpos = qpos
+        self.site_xpos = site_xpos if site_xpos is not None else np.zeros((2, 3))
+        self.xpos = xpos if xpos is not None else np.zeros((2, 3))
+        self.xquat = xquat if xquat is not None else np.zeros((2, 4))
+
+    def replace(self, **kw):
+        return FakeData(kw.get("qpos", self.qpos), kw.get("site_xpos", self.site_xpos), kw.get("xpos", self.xpos), kw.get("xquat", self.xquat))
+
+
+class FakeModel:
+    def __init__(self, nq, jnt_type, site_pos):
+        self.nq, self.jnt_type, self.site_pos = nq, jnt_type, site_pos
+
+    def replace(self, **kw):
+        m = FakeModel(self.nq, self.jnt_type, self.site_pos)
+        m.__dict__.update(kw)
+        return m
+
+
+class FakeStacCore:
+    def __init__(self):
+        self.q_calls, self.m_calls, self.q0_args = 0, 0, []
+
+    def q_opt(self, *args, **kwargs):
+        self.q_calls += 1
+        q0 = args[5]
+        self.q0_args.append(np.array(q0))
+        return args[1], types.SimpleNamespace(params=q0, state=types.SimpleNamespace(error=0.0))
+
+    def m_opt(self, mjx_model, mjx_data, keypoints, q, initial_offsets, *args, **kwargs):
+        self.m_calls += 1
+        return types.SimpleNamespace(params=np.asarray(initial_offsets).reshape(-1, 3), error=0.0)
+
+
+def test_root_optimization_calls_q_opt_twice_and_seeds_translation():
+    core = FakeStacCore()
+    mdl = FakeModel(7, np.array([0]), np.zeros((2, 3)))
+    data = FakeData(np.array([91.0, 92.0, 93.0, 4.0, 5.0, 6.0, 7.0]))
+    kp = np.array([[11.0, 12.0, 13.0, 21.0, 22.0, 23.0]])
+    out = compute_stac.root_optimization(core, mdl, data, kp, 1, np.zeros(7), np.ones(7), np.array([0, 1]), np.array([True, True]))
+    assert isinstance(out, FakeData) and core.q_calls == 2
+    expected = np.array([21.0, 22.0, 23.0, 4.0, 5.0, 6.0, 7.0])
+    np.testing.assert_allclose(core.q0_args[0], expected)
+    np.testing.assert_allclose(core.q0_args[1], expected)
+
+
+def test_offset_optimization_calls_m_opt_once_and_writes_site_pos():
+    core = FakeStacCore()
+    mdl = FakeModel(7, np.array([0]), np.zeros((2, 3)))
+    offsets = np.zeros((2, 3))
+    mdl2, data2, off = compute_stac.offset_optimization(
+        core, mdl, FakeData(np.zeros(7)), np.zeros((4, 6)), offsets, np.zeros((4, 7)), 2, np.zeros((2, 3)), np.array([0, 1]), 0.0
+    )
+    assert core.m_calls == 1
+    np.testing.assert_allclose(off, offsets)
+    np.testing.assert_allclose(mdl2.site_pos, offsets)
+
+
+def test_pose_optimization_runs_all_frames_through_the_seam():
+    core = FakeStacCore()
+    mdl = FakeModel(7, np.array([0]), np.zeros((2, 3)))
+    res = compute_stac.pose_optimization(core, mdl, FakeData(np.zeros(7)), np.zeros((2, 6)), np.zeros(7), np.ones(7), np.array([0, 1]), [])
+    _, qposes, _, _, marker_sites, _, frame_error = res
+    assert qposes.shape == (2, 7) and len(marker_sites) == 2 and len(frame_error) == 2
+    assert core.q_calls == 2
+    core = FakeStacCore()
+    parts = [np.array([1, 1, 1, 0, 0, 0, 0], bool), np.array([0, 0, 0, 1, 1, 1, 1], bool)]
+    compute_stac.pose_optimization(core, mdl, FakeData(np.zeros(7)), np.zeros((3, 6)), np.zeros(7), np.ones(7), np.array([0, 1]), parts)
+    assert core.q_calls == 3 * (1 + 2)  # 1 + P solves per frame (compute_stac.py:219-250)
+
+
+def test_sample_time_indices_covers_all_frames_when_sample_exceeds_clip():
+    idx = compute_stac.sample_time_indices(10, 100)
+    assert sorted(idx.tolist()) == list(range(10))
+    idx = compute_stac.sample_time_indices(1000, 100)
+    assert len(idx) == 100 and len(set(idx.tolist())) == 100
+
+
+def test_package_layout_quirk_of_batched_runs():
+    """reference stac.py:483-486: xpos/xquat flattened clip-major (order='F' on [F,C,...]) but marker_sites
+    flattened with a C-order reshape of [F,C,K,3], i.e. frame-major interleave."""
+    from stac_mjx_b200.stac import Stac
+
+    C, F, nb, K, nq = 3, 4, 2, 2, 5
+    tag = lambda c, f: 100 * c + f
+    qposes = np.array([[[tag(c, f)] * nq for f in range(F)] for c in range(C)], np.float32)
+    xposes = np.array([[[[tag(c, f)] * 3] * nb for c in range(C)] for f in range(F)], np.float32)  # [F,C,nb,3]
+    xquats = np.array([[[[tag(c, f)] * 4] * nb for c in range(C)] for f in range(F)], np.float32)
+    sites = np.array([[[[tag(c, f)] * 3] * K for c in range(C)] for f in range(F)], np.float32)
+    kp = np.zeros((C, F, 3 * K), np.float32)
+    fake = types.SimpleNamespace(_part_names=["q"] * nq, _body_names=["b"] * nb, _kp_names=["k"] * K, _offsets=None)
+    mdl = types.SimpleNamespace(site_pos=types.SimpleNamespace(cpu=lambda: types.SimpleNamespace(numpy=lambda: np.zeros((K, 3)))))
+    d = Stac._package_data(fake, mdl, qposes, xposes, xquats, sites, kp, batched=True)
+    clip_major = [tag(c, f) for c in range(C) for f in range(F)]
+    frame_major = [tag(c, f) for f in range(F) for c in range(C)]
+    assert d.qpos[:, 0].tolist() == clip_major
+    assert d.xpos[:, 0, 0].tolist() == clip_major and d.xquat[:, 0, 0].tolist() == clip_major
+    assert d.marker_sites[:, 0, 0].tolist() == frame_major
+    assert d.kp_data.shape == (C * F, 3 * K)
+
+
+def test_run_stac_rejects_bad_column_count_and_indivisible_clips(monkeypatch):
+    cfg = config.Cfg({"model": {"MJCF_PATH": "x.xml"}, "stac": {"fit_offsets_path": "a.h5", "ik_only_path": "b.h5", "skip_fit_offsets": True,
+                                                                  "skip_ik_only": False, "n_frames_per_clip": 4, "n_fit_frames": 2}})  # fmt: skip
+    with pytest.raises(ValueError, match="columns but expected"):
+        main.run_stac(cfg, np.zeros((8, 5), np.float32), ["a", "b"])
+
+    class DummyStac:
+        def __init__(self, *a, **k):
+            pass
+
+    monkeypatch.setattr(main, "Stac", DummyStac)
+    with pytest.raises(ValueError, match="must divide evenly"):
+        main.run_stac(cfg, np.zeros((10, 6), np.float32), ["a", "b"])
+    cfg.stac.skip_ik_only = True
+    fit_path, ik_path = main.run_stac(cfg, np.zeros((10, 6), np.float32), ["a", "b"])
+    assert ik_path is None and str(fit_path).endswith("a.h5")
+
+
+def test_config_composer_reads_a_hydra_style_tree(tmp_path):
+    (tmp_path / "model").mkdir()
+    (tmp_path / "stac").mkdir()
+    (tmp_path / "config.yaml").write_text("defaults:\n  - stac: demo\n  - model: toy\n  - _self_\n")
+    (tmp_path / "model" / "toy.yaml").write_text("MJCF_PATH: m.xml\nFTOL: 1.0e-4\nN_ITER_Q: 400\nKEYPOINT_MODEL_PAIRS: {a: b}\n")
+    (tmp_path / "model" / "other.yaml").write_text("MJCF_PATH: o.xml\n")
+    (tmp_path / "stac" / "demo.yaml").write_text("n_frames_per_clip: 250\ncontinuous: False\nmujoco: {solver: newton}\n")
+    cfg = config._compose_yaml(tmp_path, "config", [])
+    assert cfg.model.MJCF_PATH == "m.xml" and cfg.stac.n_frames_per_clip == 250 and cfg.stac.mujoco.solver == "newton"
+    assert "ROOT_OPTIMIZATION_KEYPOINT" not in cfg.model and cfg.model.get("SITES_TO_REGULARIZE", []) == []
+    cfg = config._compose_yaml(tmp_path, "config", ["model=other", "stac.n_frames_per_clip=10"])
+    assert cfg.model.MJCF_PATH == "o.xml" and cfg.stac.n_frames_per_clip == 10
+
+
+def test_shard_range_partitions_contiguously():
+    for n in (0, 1, 7, 72, 73):
+        for ws in (1, 2, 3, 8):
+            blocks = [parallel.shard_range(n, r, ws) for r in range(ws)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_edge_effect_crossfade_shapes():
+    n_clip, F, ov = 3, 20, utils.CONTINUOUS_BATCH_OVERLAP
+    mk = lambda *tail: np.random.default_rng(0).normal(size=(n_clip * (F + ov),) + tail)
+    d = io.StacData(qpos=mk(5), xpos=mk(2, 3), xquat=mk(2, 4), marker_sites=mk(2, 3), offsets=np.zeros((2, 3)), kp_data=mk(6),
+                    names_qpos=[], names_xpos=[], kp_names=[])  # fmt: skip
+    out = utils.handle_edge_effects(d, F)
+    assert out.qpos.shape == (n_clip * F, 5) and out.xpos.shape == (n_clip * F, 2, 3)
