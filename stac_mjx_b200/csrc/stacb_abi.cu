@@ -163,6 +163,7 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   for (size_t e = 0; e < full.size(); e++) loc_f[full[e]] = (int)e;
   for (int p = 0; p < K; p++) { se_a[p] = loc_a[m.site_body[order[p]]]; se_f[p] = loc_f[m.site_body[order[p]]]; }
   DevTree &T = t->T;
+  if (ra > RMAX || rf > RMAX) { delete t; return fail(STACB_E_UNSUPPORTED, "tree deeper than 256 levels"); }
   T.nbody = nb; T.nq = m.nq; T.njnt = m.njnt; T.K = K; T.spl = std::max(1, (K + 31) / 32);
   T.act.n = (int)act.size(); T.act.rounds = ra;
   T.full.n = (int)full.size(); T.full.rounds = rf;
@@ -170,6 +171,16 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   if ((rc = upload(t, rec_a, &T.act.rec)) || (rc = upload(t, anc_a, &T.act.anc)) || (rc = upload(t, rec_f, &T.full.rec)) ||
       (rc = upload(t, anc_f, &T.full.anc)) || (rc = upload(t, order, &T.site_order)) || (rc = upload(t, se_a, &T.site_eact)) ||
       (rc = upload(t, se_f, &T.site_efull))) {
+    stacb_tree_destroy(t);
+    return rc;
+  }
+  std::vector<int> qadr;
+  for (int j = 0; j < m.njnt; j++) {
+    if (m.jnt_type[j] == STACB_JNT_FREE) qadr.push_back(m.jnt_qposadr[j] + 3);
+    if (m.jnt_type[j] == STACB_JNT_BALL) qadr.push_back(m.jnt_qposadr[j]);
+  }
+  T.nquat = (int)qadr.size();
+  if ((rc = upload(t, qadr, &T.quat_adr))) {
     stacb_tree_destroy(t);
     return rc;
   }

@@ -37,6 +37,8 @@ struct DevTree {
   const int *site_eact;   // [K] by sorted position: active-set index of the site's body
   const int *site_efull;  // [K] by sorted position: full-set index of the site's body
   int nqp, pqn, npre;     // per-chain shared memory: qbuf[nqp] gbuf[nqp] PQ[pqn*7] Ipre[npre*6]
+  int nquat;              // free / ball joints of the whole model
+  const int *quat_adr;    // [nquat] qpos address of each quaternion
 };
 
 __host__ __device__ inline int chain_smem_floats(const DevTree &T) { return 2 * T.nqp + 7 * T.pqn + 6 * T.npre; }
@@ -57,6 +59,59 @@ __device__ __forceinline__ float ldf(const int *p) { return __int_as_float(__ldg
 __device__ __forceinline__ V3 ldv3(const int *p) { return mk3(ldf(p), ldf(p + 1), ldf(p + 2)); }
 __device__ __forceinline__ V3 lds3(const float *p) { return mk3(p[0], p[1], p[2]); }
 __device__ __forceinline__ Q4 lds4(const float *p) { return mk4(p[0], p[1], p[2], p[3]); }
+__device__ __forceinline__ void sts7(float *o, V3 p, Q4 q) { o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = q.w; o[4] = q.x; o[5] = q.y; o[6] = q.z; }
+__device__ __forceinline__ V3 shfl3(V3 v, int src) {
+  return mk3(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src));
+}
+__device__ __forceinline__ Q4 shfl4(Q4 q, int src) {
+  return mk4(__shfl_sync(0xffffffffu, q.w, src), __shfl_sync(0xffffffffu, q.x, src), __shfl_sync(0xffffffffu, q.y, src),
+             __shfl_sync(0xffffffffu, q.z, src));
+}
+
+// One body's constants (a record of the tree descriptor). On the hot path these live in registers for
+// the whole kernel (the lane <-> body mapping never changes); cold paths load them on demand.
+struct BodyConst {
+  V3 pos; Q4 quat;
+  int nj, parent, body;
+  int jtype[JMAX], jadr[JMAX], jsa[JMAX], jse[JMAX];
+  V3 jpos[JMAX], jaxis[JMAX];
+  float jref[JMAX];
+};
+
+__device__ __forceinline__ void load_body(BodyConst &b, const int *__restrict__ r) {
+  b.pos = ldv3(r + R_POS);
+  b.quat = mk4(ldf(r + R_QUAT), ldf(r + R_QUAT + 1), ldf(r + R_QUAT + 2), ldf(r + R_QUAT + 3));
+  b.nj = __ldg(r + R_NJNT); b.parent = __ldg(r + R_PARENT); b.body = __ldg(r + R_BODY);
+#pragma unroll
+  for (int jj = 0; jj < JMAX; jj++) {
+    const int *jr = r + R_JNT + J_STRIDE * jj;
+    b.jtype[jj] = __ldg(jr + J_TYPE); b.jadr[jj] = __ldg(jr + J_ADR); b.jsa[jj] = __ldg(jr + J_SA); b.jse[jj] = __ldg(jr + J_SE);
+    b.jpos[jj] = ldv3(jr + J_POS); b.jaxis[jj] = ldv3(jr + J_AXIS); b.jref[jj] = ldf(jr + J_REF);
+  }
+}
+
+constexpr int RMAX = 8;  // pointer-jumping rounds kept in registers (tree depth <= 256)
+
+// Register-resident view of the ACTIVE body set for one lane.
+template <int NB>
+struct Hot {
+  BodyConst bc[NB];
+  int anc[NB][RMAX];
+  bool on[NB];
+};
+
+template <int NB>
+__device__ __forceinline__ void hot_init(Hot<NB> &H, const DevSet &S, int lane) {
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    const int e = lane + 32 * i;
+    H.on[i] = e < S.n;
+    load_body(H.bc[i], S.rec + (size_t)(H.on[i] ? e : 0) * REC);
+    if (!H.on[i]) H.bc[i].nj = 0;
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) H.anc[i][r] = (H.on[i] && r < S.rounds) ? __ldg(S.anc + r * S.n + e) : -1;
+  }
+}
 
 // Per-lane results of the local phase that the reverse sweep needs.
 template <int NB>
@@ -66,69 +121,141 @@ struct Keep {
   float fnorm[NB];      // divisor of the quaternion normalisation (free / ball joint)
 };
 
+template <int NB>
+struct FkState {
+  V3 P[NB];
+  Q4 Q[NB];
+  Keep<NB> keep;
+};
+
 // MJX smooth.kinematics per-body step, evaluated in the parent's frame (canonical order).
 template <int NB, bool KEEP>
-__device__ __forceinline__ void fk_local(const int *__restrict__ r, float *qbuf, V3 &pos, Q4 &quat, Keep<NB> *keep, int slot) {
-  pos = ldv3(r + R_POS);
-  quat = mk4(ldf(r + R_QUAT), ldf(r + R_QUAT + 1), ldf(r + R_QUAT + 2), ldf(r + R_QUAT + 3));
-  const int nj = __ldg(r + R_NJNT);
+__device__ __forceinline__ void fk_local(const BodyConst &b, float *qbuf, V3 &pos, Q4 &quat, Keep<NB> *keep, int slot) {
+  pos = b.pos;
+  quat = b.quat;
+  // half-angle sines / cosines of all hinges first: independent chains the scheduler can interleave
+  float sn[JMAX], cs[JMAX];
 #pragma unroll
   for (int jj = 0; jj < JMAX; jj++) {
-    if (jj < nj) {
-      const int *jr = r + R_JNT + J_STRIDE * jj;
-      const int type = __ldg(jr + J_TYPE), adr = __ldg(jr + J_ADR);
-      const V3 jpos = ldv3(jr + J_POS), jaxis = ldv3(jr + J_AXIS);
-      V3 anchor, axis;
-      if (type == STACB_JNT_FREE) {
-        anchor = lds3(qbuf + adr);
-        axis = mk3(0.f, 0.f, 1.f);
-      } else {
-        anchor = add3(rotate(jpos, quat), pos);
-        axis = rotate(jaxis, quat);
-      }
-      if (KEEP) { keep->anchor[slot][jj] = anchor; keep->axis[slot][jj] = axis; }
-      if (type == STACB_JNT_FREE) {
+    sn[jj] = 0.f; cs[jj] = 1.f;
+    if (jj < b.nj && b.jtype[jj] == STACB_JNT_HINGE) sincos_canon((qbuf[b.jadr[jj]] - b.jref[jj]) * 0.5f, &sn[jj], &cs[jj]);
+  }
+#pragma unroll
+  for (int jj = 0; jj < JMAX; jj++) {
+    if (jj < b.nj) {
+      const int type = b.jtype[jj], adr = b.jadr[jj];
+      const V3 jpos = b.jpos[jj], jaxis = b.jaxis[jj];
+      if (type == STACB_JNT_HINGE) {
+        const V3 anchor = add3(rotate(jpos, quat), pos);
+        if (KEEP) { keep->anchor[slot][jj] = anchor; keep->axis[slot][jj] = rotate(jaxis, quat); }
+        quat = qmul(quat, mk4(cs[jj], jaxis.x * sn[jj], jaxis.y * sn[jj], jaxis.z * sn[jj]));
+        pos = sub3(anchor, rotate(jpos, quat));
+      } else if (type == STACB_JNT_FREE) {
         float d;
-        pos = anchor;
+        pos = lds3(qbuf + adr);
+        if (KEEP) { keep->anchor[slot][jj] = pos; keep->axis[slot][jj] = mk3(0.f, 0.f, 1.f); }
         quat = normalize4(lds4(qbuf + adr + 3), &d);
         qbuf[adr + 3] = quat.w; qbuf[adr + 4] = quat.x; qbuf[adr + 5] = quat.y; qbuf[adr + 6] = quat.z;
         if (KEEP) keep->fnorm[slot] = d;
       } else if (type == STACB_JNT_BALL) {
         float d;
-        Q4 ql = normalize4(lds4(qbuf + adr), &d);
+        const V3 anchor = add3(rotate(jpos, quat), pos);
+        if (KEEP) { keep->anchor[slot][jj] = anchor; keep->axis[slot][jj] = rotate(jaxis, quat); }
+        const Q4 ql = normalize4(lds4(qbuf + adr), &d);
         qbuf[adr] = ql.w; qbuf[adr + 1] = ql.x; qbuf[adr + 2] = ql.y; qbuf[adr + 3] = ql.z;
         if (KEEP) keep->fnorm[slot] = d;
         quat = qmul(quat, ql);
         pos = sub3(anchor, rotate(jpos, quat));
-      } else if (type == STACB_JNT_HINGE) {
-        Q4 ql = axis_angle(jaxis, qbuf[adr] - ldf(jr + J_REF));
-        quat = qmul(quat, ql);
-        pos = sub3(anchor, rotate(jpos, quat));
       } else {  // slide
-        float d = qbuf[adr] - ldf(jr + J_REF);
+        const V3 axis = rotate(jaxis, quat);
+        if (KEEP) { keep->anchor[slot][jj] = add3(rotate(jpos, quat), pos); keep->axis[slot][jj] = axis; }
+        const float d = qbuf[adr] - b.jref[jj];
         pos = mk3(fmaf(axis.x, d, pos.x), fmaf(axis.y, d, pos.y), fmaf(axis.z, d, pos.z));
       }
     }
   }
 }
 
-// FK over a body set. On return PQ[e*7..] holds the world pose of every set element and
-// P/Q the poses of this lane's slots. Reads the point from ch.qbuf (quaternions normalised in place).
+// Hot-path FK over the active set: constants from registers; with one body per lane the pointer-jumping
+// rounds exchange poses by warp shuffles, otherwise through the PQ buffer in shared memory.
 template <int NB, bool KEEP>
-__device__ __forceinline__ void fk_set(const Chain &ch, const DevSet &S, V3 (&P)[NB], Q4 (&Q)[NB], Keep<NB> *keep) {
+__device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkState<NB> &S) {
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    S.P[i] = mk3(0.f, 0.f, 0.f); S.Q[i] = mk4(1.f, 0.f, 0.f, 0.f);
+    if (H.on[i]) fk_local<NB, KEEP>(H.bc[i], ch.qbuf, S.P[i], S.Q[i], &S.keep, i);
+  }
+  const int rounds = ch.T.act.rounds;
+  if constexpr (NB == 1) {
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) {
+      if (r < rounds) {
+        const int a = H.anc[0][r];
+        const int src = (a >= 0) ? a : ch.lane;
+        const V3 pa = shfl3(S.P[0], src);
+        const Q4 qa = shfl4(S.Q[0], src);
+        if (a >= 0) { S.P[0] = add3(pa, rotate(S.P[0], qa)); S.Q[0] = qmul(qa, S.Q[0]); }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) {
+      if (r < rounds) {
+#pragma unroll
+        for (int i = 0; i < NB; i++)
+          if (H.on[i]) sts7(ch.PQ + 7 * (ch.lane + 32 * i), S.P[i], S.Q[i]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+          const int a = H.anc[i][r];
+          if (a >= 0) {
+            const float *o = ch.PQ + 7 * a;
+            const V3 pa = lds3(o);
+            const Q4 qa = lds4(o + 3);
+            S.P[i] = add3(pa, rotate(S.P[i], qa));
+            S.Q[i] = qmul(qa, S.Q[i]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+      if (H.on[i]) sts7(ch.PQ + 7 * (ch.lane + 32 * i), S.P[i], S.Q[i]);
+    __syncwarp();
+  }
+}
+
+// World pose of active-set element e. Warp-collective when NB == 1 (every lane must call it).
+template <int NB>
+__device__ __forceinline__ void gather_pose(const Chain &ch, const FkState<NB> &S, int e, V3 &p, Q4 &q) {
+  if constexpr (NB == 1) {
+    p = shfl3(S.P[0], e);
+    q = shfl4(S.Q[0], e);
+  } else {
+    const float *o = ch.PQ + 7 * e;
+    p = lds3(o);
+    q = lds4(o + 3);
+  }
+}
+
+// Cold-path FK over any body set with constants read from global memory; results in PQ (shared memory).
+template <int NB>
+__device__ __forceinline__ void fk_cold(const Chain &ch, const DevSet &S, V3 (&P)[NB], Q4 (&Q)[NB]) {
 #pragma unroll
   for (int i = 0; i < NB; i++) {
     const int e = ch.lane + 32 * i;
-    if (e < S.n) fk_local<NB, KEEP>(S.rec + (size_t)e * REC, ch.qbuf, P[i], Q[i], keep, i);
+    if (e < S.n) {
+      BodyConst b;
+      load_body(b, S.rec + (size_t)e * REC);
+      fk_local<NB, false>(b, ch.qbuf, P[i], Q[i], nullptr, i);
+    }
   }
   for (int r = 0; r < S.rounds; r++) {
 #pragma unroll
     for (int i = 0; i < NB; i++) {
       const int e = ch.lane + 32 * i;
-      if (e < S.n) {
-        float *o = ch.PQ + 7 * e;
-        o[0] = P[i].x; o[1] = P[i].y; o[2] = P[i].z; o[3] = Q[i].w; o[4] = Q[i].x; o[5] = Q[i].y; o[6] = Q[i].z;
-      }
+      if (e < S.n) sts7(ch.PQ + 7 * e, P[i], Q[i]);
     }
     __syncwarp();
 #pragma unroll
@@ -150,10 +277,7 @@ __device__ __forceinline__ void fk_set(const Chain &ch, const DevSet &S, V3 (&P)
 #pragma unroll
   for (int i = 0; i < NB; i++) {
     const int e = ch.lane + 32 * i;
-    if (e < S.n) {
-      float *o = ch.PQ + 7 * e;
-      o[0] = P[i].x; o[1] = P[i].y; o[2] = P[i].z; o[3] = Q[i].w; o[4] = Q[i].x; o[5] = Q[i].y; o[6] = Q[i].z;
-    }
+    if (e < S.n) sts7(ch.PQ + 7 * e, P[i], Q[i]);
   }
   __syncwarp();
 }
@@ -166,6 +290,12 @@ struct Sites {
   V3 off[SPL];     // site offset in the body frame (site_pos)
   V3 kp[SPL];      // observed keypoint
   V3 km[SPL];      // 0/1 mask per coordinate
+};
+
+template <int SPL>
+struct SiteVals {
+  V3 s[SPL];    // marker site world position
+  V3 res[SPL];  // masked residual
 };
 
 template <int SPL>
@@ -213,120 +343,124 @@ __device__ __forceinline__ void sites_mask_kp(Sites<SPL> &st, const uint8_t *__r
     }
 }
 
-// Marker sites from the poses in PQ, masked residual, loss; optionally the inclusive prefix of
-// the per-site wrench (force, torque about cref) into Ipre for the reverse sweep.
-template <int SPL, bool FULLSET>
-__device__ __forceinline__ float sites_loss(const Chain &ch, const Sites<SPL> &st, bool need_grad, V3 *site_out /*[SPL] or null*/) {
+// Marker sites from the active-set poses, masked residuals and the loss (q_loss, stac_core.py:57-63).
+template <int NB, int SPL>
+__device__ __forceinline__ float sites_loss(const Chain &ch, const FkState<NB> &S, const Sites<SPL> &st, SiteVals<SPL> &sv) {
   float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < SPL; i++) {
+    V3 pb;
+    Q4 qb;
+    gather_pose<NB>(ch, S, st.k[i] >= 0 ? st.eact[i] : 0, pb, qb);
+    sv.s[i] = mk3(0.f, 0.f, 0.f); sv.res[i] = mk3(0.f, 0.f, 0.f);
+    if (st.k[i] >= 0) {
+      const V3 s = add3(pb, rotate(st.off[i], qb));
+      const V3 res = mk3((st.kp[i].x - s.x) * st.km[i].x, (st.kp[i].y - s.y) * st.km[i].y, (st.kp[i].z - s.z) * st.km[i].z);
+      sv.s[i] = s; sv.res[i] = res;
+      const float e = fmaf(res.z, res.z, fmaf(res.y, res.y, res.x * res.x));
+      acc = (i == 0) ? e : acc + e;
+    }
+  }
+  return warp_sum(acc);
+}
+
+// Inclusive prefix (over sites sorted by body) of the per-site wrench (force, torque about cref) -> Ipre.
+template <int SPL>
+__device__ __forceinline__ void wrench_prefix(const Chain &ch, const Sites<SPL> &st, const SiteVals<SPL> &sv, V3 cref) {
   float w[SPL][6];
   float run[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  V3 cref = mk3(0.f, 0.f, 0.f);
-  if (need_grad) cref = lds3(ch.PQ);
 #pragma unroll
   for (int i = 0; i < SPL; i++) {
     if (st.k[i] >= 0) {
-      const float *o = ch.PQ + 7 * (FULLSET ? st.efull[i] : st.eact[i]);
-      const V3 s = add3(lds3(o), rotate(st.off[i], lds4(o + 3)));
-      if (site_out) site_out[i] = s;
-      const V3 res = mk3((st.kp[i].x - s.x) * st.km[i].x, (st.kp[i].y - s.y) * st.km[i].y, (st.kp[i].z - s.z) * st.km[i].z);
-      const float e = fmaf(res.z, res.z, fmaf(res.y, res.y, res.x * res.x));
-      acc = (i == 0) ? e : acc + e;
-      if (need_grad) {
-        const V3 f = mk3(-2.0f * (st.km[i].x * res.x), -2.0f * (st.km[i].y * res.y), -2.0f * (st.km[i].z * res.z));
-        const V3 tq = cross3(sub3(s, cref), f);
-        const float v[6] = {f.x, f.y, f.z, tq.x, tq.y, tq.z};
+      const V3 res = sv.res[i];
+      const V3 f = mk3(-2.0f * (st.km[i].x * res.x), -2.0f * (st.km[i].y * res.y), -2.0f * (st.km[i].z * res.z));
+      const V3 tq = cross3(sub3(sv.s[i], cref), f);
+      const float v[6] = {f.x, f.y, f.z, tq.x, tq.y, tq.z};
 #pragma unroll
-        for (int c = 0; c < 6; c++) { run[c] = (i == 0) ? v[c] : run[c] + v[c]; w[i][c] = run[c]; }
-      }
+      for (int c = 0; c < 6; c++) { run[c] = (i == 0) ? v[c] : run[c] + v[c]; w[i][c] = run[c]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; c++) w[i][c] = 0.f;
     }
   }
-  const float loss = warp_sum(acc);
-  if (need_grad) {
-    float tot[6];
+  float tot[6];
 #pragma unroll
-    for (int c = 0; c < 6; c++) tot[c] = run[c];
+  for (int c = 0; c < 6; c++) tot[c] = run[c];
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-#pragma unroll
-      for (int c = 0; c < 6; c++) {
-        const float up = __shfl_up_sync(0xffffffffu, tot[c], off);
-        if (ch.lane >= off) tot[c] = tot[c] + up;
-      }
-    }
+  for (int off = 1; off < 32; off <<= 1) {
 #pragma unroll
     for (int c = 0; c < 6; c++) {
-      const float ex = __shfl_up_sync(0xffffffffu, tot[c], 1);
+      const float up = __shfl_up_sync(0xffffffffu, tot[c], off);
+      if (ch.lane >= off) tot[c] = tot[c] + up;
+    }
+  }
 #pragma unroll
-      for (int i = 0; i < SPL; i++) {
-        if (st.k[i] >= 0) {
-          const float val = (ch.lane >= 1) ? ex + w[i][c] : w[i][c];
-          ch.Ipre[6 * (ch.lane * ch.T.spl + i) + c] = val;
-        }
+  for (int c = 0; c < 6; c++) {
+    const float ex = __shfl_up_sync(0xffffffffu, tot[c], 1);
+#pragma unroll
+    for (int i = 0; i < SPL; i++) {
+      if (st.k[i] >= 0) {
+        const float val = (ch.lane >= 1) ? ex + w[i][c] : w[i][c];
+        ch.Ipre[6 * (ch.lane * ch.T.spl + i) + c] = val;
       }
     }
-    __syncwarp();
   }
-  return loss;
+  __syncwarp();
 }
 
-// Reverse sweep: each body lane turns the subtree wrench of its joints into d loss / d qpos.
+// Reverse sweep: each body lane turns the subtree wrench of its joints into d loss / d qpos (into gbuf).
 template <int NB>
-__device__ __forceinline__ void joint_grads(const Chain &ch, const DevSet &S, const V3 (&P)[NB], const Q4 (&Q)[NB], const Keep<NB> &keep) {
-  const V3 cref = lds3(ch.PQ);
+__device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, const FkState<NB> &S, V3 cref) {
 #pragma unroll
   for (int i = 0; i < NB; i++) {
-    const int e = ch.lane + 32 * i;
-    if (e < S.n) {
-      const int *r = S.rec + (size_t)e * REC;
-      const int nj = __ldg(r + R_NJNT), par = __ldg(r + R_PARENT);
+    const BodyConst &b = H.bc[i];
+    V3 pp;
+    Q4 pq;
+    gather_pose<NB>(ch, S, b.parent >= 0 ? b.parent : 0, pp, pq);
 #pragma unroll
-      for (int jj = 0; jj < JMAX; jj++) {
-        if (jj < nj) {
-          const int *jr = r + R_JNT + J_STRIDE * jj;
-          const int type = __ldg(jr + J_TYPE), adr = __ldg(jr + J_ADR), sa = __ldg(jr + J_SA), se = __ldg(jr + J_SE);
-          if (se > sa) {
-            float wr[6];
+    for (int jj = 0; jj < JMAX; jj++) {
+      if (jj < b.nj) {
+        const int type = b.jtype[jj], adr = b.jadr[jj], sa = b.jsa[jj], se = b.jse[jj];
+        if (se > sa) {
+          float wr[6];
 #pragma unroll
-            for (int c = 0; c < 6; c++) {
-              const float hi = ch.Ipre[6 * (se - 1) + c];
-              wr[c] = (sa > 0) ? hi - ch.Ipre[6 * (sa - 1) + c] : hi;
+          for (int c = 0; c < 6; c++) {
+            const float hi = ch.Ipre[6 * (se - 1) + c];
+            wr[c] = (sa > 0) ? hi - ch.Ipre[6 * (sa - 1) + c] : hi;
+          }
+          const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
+          if (type == STACB_JNT_HINGE || type == STACB_JNT_SLIDE || type == STACB_JNT_BALL) {
+            V3 A = S.keep.anchor[i][jj], W = S.keep.axis[i][jj];
+            if (b.parent >= 0) {
+              A = add3(pp, rotate(A, pq));
+              W = rotate(W, pq);
             }
-            const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
-            if (type == STACB_JNT_FREE) {
-              const V3 Tp = sub3(Tq, cross3(sub3(P[i], cref), F));
-              ch.gbuf[adr] = F.x; ch.gbuf[adr + 1] = F.y; ch.gbuf[adr + 2] = F.z;
-              const Q4 qh = Q[i];
-              Q4 h = qmul(mk4(0.f, Tp.x, Tp.y, Tp.z), qh);
-              h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
-              const float pr = fmaf(qh.z, h.z, fmaf(qh.y, h.y, fmaf(qh.x, h.x, qh.w * h.w))), n = keep.fnorm[i];
-              ch.gbuf[adr + 3] = fmaf(-qh.w, pr, h.w) / n; ch.gbuf[adr + 4] = fmaf(-qh.x, pr, h.x) / n;
-              ch.gbuf[adr + 5] = fmaf(-qh.y, pr, h.y) / n; ch.gbuf[adr + 6] = fmaf(-qh.z, pr, h.z) / n;
+            if (type == STACB_JNT_SLIDE) {
+              ch.gbuf[adr] = dot3(W, F);
             } else {
-              V3 A = keep.anchor[i][jj], W = keep.axis[i][jj];
-              if (par >= 0) {
-                const float *o = ch.PQ + 7 * par;
-                const Q4 pq = lds4(o + 3);
-                A = add3(lds3(o), rotate(A, pq));
-                W = rotate(W, pq);
-              }
-              if (type == STACB_JNT_SLIDE) {
-                ch.gbuf[adr] = dot3(W, F);
-              } else {
-                const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
-                if (type == STACB_JNT_HINGE) {
-                  ch.gbuf[adr] = dot3(W, Ta);
-                } else {  // ball (must be the last joint of its body)
-                  const Q4 qb = Q[i];
-                  const V3 tl = rotate(Ta, mk4(qb.w, -qb.x, -qb.y, -qb.z));
-                  const Q4 ql = lds4(ch.qbuf + adr);
-                  Q4 h = qmul(ql, mk4(0.f, tl.x, tl.y, tl.z));
-                  h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
-                  const float pr = fmaf(ql.z, h.z, fmaf(ql.y, h.y, fmaf(ql.x, h.x, ql.w * h.w))), n = keep.fnorm[i];
-                  ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) / n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) / n;
-                  ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) / n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) / n;
-                }
+              const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
+              if (type == STACB_JNT_HINGE) {
+                ch.gbuf[adr] = dot3(W, Ta);
+              } else {  // ball (must be the last joint of its body)
+                const Q4 qb = S.Q[i];
+                const V3 tl = rotate(Ta, mk4(qb.w, -qb.x, -qb.y, -qb.z));
+                const Q4 ql = lds4(ch.qbuf + adr);
+                Q4 h = qmul(ql, mk4(0.f, tl.x, tl.y, tl.z));
+                h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
+                const float pr = fmaf(ql.z, h.z, fmaf(ql.y, h.y, fmaf(ql.x, h.x, ql.w * h.w))), n = S.keep.fnorm[i];
+                ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) / n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) / n;
+                ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) / n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) / n;
               }
             }
+          } else {  // free
+            const V3 Tp = sub3(Tq, cross3(sub3(S.P[i], cref), F));
+            ch.gbuf[adr] = F.x; ch.gbuf[adr + 1] = F.y; ch.gbuf[adr + 2] = F.z;
+            const Q4 qh = S.Q[i];
+            Q4 h = qmul(mk4(0.f, Tp.x, Tp.y, Tp.z), qh);
+            h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
+            const float pr = fmaf(qh.z, h.z, fmaf(qh.y, h.y, fmaf(qh.x, h.x, qh.w * h.w))), n = S.keep.fnorm[i];
+            ch.gbuf[adr + 3] = fmaf(-qh.w, pr, h.w) / n; ch.gbuf[adr + 4] = fmaf(-qh.x, pr, h.x) / n;
+            ch.gbuf[adr + 5] = fmaf(-qh.y, pr, h.y) / n; ch.gbuf[adr + 6] = fmaf(-qh.z, pr, h.z) / n;
           }
         }
       }
@@ -342,25 +476,31 @@ struct Coords {
   bool valid[CPL];
 };
 
-// q_loss at `pt` (stac_core.py:27-63). mask bit m set <=> slot m is optimised; elsewhere q0 is used.
+// Forward half of q_loss at `pt` (stac_core.py:27-63): FK state, marker residuals, loss.
+// mask bit m set <=> slot m is optimised; elsewhere q0 is used (utils.make_qs).
 template <int CPL, int NB, int SPL>
-__device__ __forceinline__ float eval_point(const Chain &ch, const Coords<CPL> &co, const float (&pt)[CPL], const float (&q0)[CPL],
-                                            unsigned maskbits, const Sites<SPL> &st, bool need_grad, float (&g)[CPL]) {
+__device__ __forceinline__ float eval_fwd(const Chain &ch, const Coords<CPL> &co, const Hot<NB> &H, const float (&pt)[CPL],
+                                          const float (&q0)[CPL], unsigned maskbits, const Sites<SPL> &st, FkState<NB> &S,
+                                          SiteVals<SPL> &sv) {
 #pragma unroll
   for (int m = 0; m < CPL; m++)
     if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = ((maskbits >> m) & 1u) ? pt[m] : q0[m];
   __syncwarp();
-  V3 P[NB];
-  Q4 Q[NB];
-  Keep<NB> keep;
-  fk_set<NB, true>(ch, ch.T.act, P, Q, &keep);
-  const float loss = sites_loss<SPL, false>(ch, st, need_grad, nullptr);
-  if (need_grad) {
-    joint_grads<NB>(ch, ch.T.act, P, Q, keep);
+  fk_hot<NB, true>(ch, H, S);
+  return sites_loss<NB, SPL>(ch, S, st, sv);
+}
+
+// Reverse half: gradient of the loss at the point of the last eval_fwd (its state is still live).
+template <int CPL, int NB, int SPL>
+__device__ __forceinline__ void eval_bwd(const Chain &ch, const Coords<CPL> &co, const Hot<NB> &H, unsigned maskbits,
+                                         const Sites<SPL> &st, const FkState<NB> &S, const SiteVals<SPL> &sv, float (&g)[CPL]) {
+  V3 cref;
+  Q4 cq;
+  gather_pose<NB>(ch, S, 0, cref, cq);
+  wrench_prefix<SPL>(ch, st, sv, cref);
+  joint_grads<NB>(ch, H, S, cref);
 #pragma unroll
-    for (int m = 0; m < CPL; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? ch.gbuf[ch.lane + 32 * m] : 0.f;
-  }
-  return loss;
+  for (int m = 0; m < CPL; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? ch.gbuf[ch.lane + 32 * m] : 0.f;
 }
 
 template <int CPL>
@@ -374,9 +514,11 @@ __device__ __forceinline__ float lane_dot(const float (&a)[CPL], const float (&b
 struct SolveOut { float err; int iters, ls; bool bad; };
 
 // jaxopt 0.8.5 ProjectedGradient.run (ProximalGradient._update_accel/_ls/_error, box projection).
+// The reference evaluates FK again for the gradient at the accepted point (grad(fun)(next_x)); the same
+// values are obtained here from the state of the accepting line-search evaluation.
 template <int CPL, int NB, int SPL>
-__device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co, const float (&q0)[CPL], unsigned maskbits,
-                                          const Sites<SPL> &st, float tol, int maxiter, int maxls, float (&x)[CPL]) {
+__device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co, const Hot<NB> &H, const float (&q0)[CPL],
+                                          unsigned maskbits, const Sites<SPL> &st, float tol, int maxiter, int maxls, float (&x)[CPL]) {
   float y[CPL], g[CPL], xn[CPL], d[CPL], gn[CPL];
 #pragma unroll
   for (int m = 0; m < CPL; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; g[m] = 0.f; gn[m] = 0.f; }
@@ -384,19 +526,28 @@ __device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co
   SolveOut out;
   out.iters = 0; out.ls = 0; out.bad = false;
   if (maxiter <= 0) { out.err = err; return out; }
+  FkState<NB> S;
+  SiteVals<SPL> sv;
   do {
-    const float fy = eval_point<CPL, NB, SPL>(ch, co, y, q0, maskbits, st, true, g);
+    const float fy = eval_fwd<CPL, NB, SPL>(ch, co, H, y, q0, maskbits, st, S, sv);
+    eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, g);
     float stp = step;
     int halv = 0;
     for (;;) {
 #pragma unroll
-      for (int m = 0; m < CPL; m++) xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
-      const float fn = eval_point<CPL, NB, SPL>(ch, co, xn, q0, maskbits, st, false, gn);
-      out.ls++;
+      for (int m = 0; m < CPL; m++) {
+        xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+        d[m] = xn[m] - y[m];
+      }
+      float sq = lane_dot<CPL>(d, d), dg = lane_dot<CPL>(d, g);
 #pragma unroll
-      for (int m = 0; m < CPL; m++) d[m] = xn[m] - y[m];
-      const float sq = warp_sum(lane_dot<CPL>(d, d));
-      const float dg = warp_sum(lane_dot<CPL>(d, g));
+      for (int off = 16; off >= 1; off >>= 1) {  // two interleaved butterflies
+        const float a = __shfl_xor_sync(0xffffffffu, sq, off), b2 = __shfl_xor_sync(0xffffffffu, dg, off);
+        sq = sq + a;
+        dg = dg + b2;
+      }
+      const float fn = eval_fwd<CPL, NB, SPL>(ch, co, H, xn, q0, maskbits, st, S, sv);
+      out.ls++;
       const float dec = stp * (fn - fy);
       const float cond = fmaf(stp, dg, 0.5f * sq);
       if (!(fn - fn == 0.0f)) out.bad = true;
@@ -409,7 +560,7 @@ __device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co
     const float beta = (t - 1.0f) / tn;
 #pragma unroll
     for (int m = 0; m < CPL; m++) y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
-    eval_point<CPL, NB, SPL>(ch, co, xn, q0, maskbits, st, true, gn);
+    eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, gn);
 #pragma unroll
     for (int m = 0; m < CPL; m++) d[m] = co.valid[m] ? clipf(xn[m] - gn[m], co.lb[m], co.ub[m]) - xn[m] : 0.f;
     err = sqrtf(warp_sum(lane_dot<CPL>(d, d)));
@@ -424,30 +575,18 @@ __device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co
 
 // replace_qs (utils.py:147-169) as far as qpos is concerned: kinematics normalises free / ball
 // quaternions in place. q holds the full qpos vector of the chain.
-template <int CPL, int NBF>
+template <int CPL>
 __device__ __forceinline__ void normalize_qpos(const Chain &ch, const Coords<CPL> &co, float (&q)[CPL]) {
+  if (ch.T.nquat == 0) return;
 #pragma unroll
   for (int m = 0; m < CPL; m++)
     if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = q[m];
   __syncwarp();
-  const DevSet &S = ch.T.full;
-#pragma unroll
-  for (int i = 0; i < NBF; i++) {
-    const int e = ch.lane + 32 * i;
-    if (e < S.n) {
-      const int *r = S.rec + (size_t)e * REC;
-      const int nj = __ldg(r + R_NJNT);
-      for (int jj = 0; jj < nj && jj < JMAX; jj++) {
-        const int *jr = r + R_JNT + J_STRIDE * jj;
-        const int type = __ldg(jr + J_TYPE);
-        if (type == STACB_JNT_FREE || type == STACB_JNT_BALL) {
-          const int a = __ldg(jr + J_ADR) + (type == STACB_JNT_FREE ? 3 : 0);
-          float dd;
-          const Q4 qn = normalize4(lds4(ch.qbuf + a), &dd);
-          ch.qbuf[a] = qn.w; ch.qbuf[a + 1] = qn.x; ch.qbuf[a + 2] = qn.y; ch.qbuf[a + 3] = qn.z;
-        }
-      }
-    }
+  for (int j = ch.lane; j < ch.T.nquat; j += 32) {
+    const int a = __ldg(ch.T.quat_adr + j);
+    float dd;
+    const Q4 qn = normalize4(lds4(ch.qbuf + a), &dd);
+    ch.qbuf[a] = qn.w; ch.qbuf[a + 1] = qn.x; ch.qbuf[a + 2] = qn.y; ch.qbuf[a + 3] = qn.z;
   }
   __syncwarp();
 #pragma unroll
@@ -486,7 +625,7 @@ __device__ __forceinline__ void full_outputs(const Chain &ch, const Coords<CPL> 
   __syncwarp();
   V3 P[NBF];
   Q4 Q[NBF];
-  fk_set<NBF, false>(ch, ch.T.full, P, Q, nullptr);
+  fk_cold<NBF>(ch, ch.T.full, P, Q);
 #pragma unroll
   for (int m = 0; m < CPL; m++)
     if (co.valid[m]) {
@@ -539,6 +678,8 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
   coords_init<CPL>(ch, co, a.lb, a.ub);
   Sites<SPL> st;
   sites_init<SPL>(ch, st, a.site_pos);
+  Hot<NB> H;
+  hot_init<NB>(H, T.act, lane);
   const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P;
   const unsigned full_bits = mask_bits_u8<CPL>(ch, co, nullptr);
   unsigned root_bits = 0;
@@ -569,10 +710,10 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
           const int i = lane + 32 * m;
           if (i < 3) q0[m] = kpc[3 * a.root_kp_idx + i];
         }
-        const SolveOut so = solve<CPL, NB, SPL>(ch, co, q0, root_bits, st, a.tol, a.maxiter, a.maxls, x);
+        const SolveOut so = solve<CPL, NB, SPL>(ch, co, H, q0, root_bits, st, a.tol, a.maxiter, a.maxls, x);
 #pragma unroll
         for (int m = 0; m < CPL; m++) q[m] = ((root_bits >> m) & 1u) ? x[m] : q0[m];
-        normalize_qpos<CPL, NBF>(ch, co, q);
+        normalize_qpos<CPL>(ch, co, q);
         bad |= so.bad;
         if (a.root_stats && lane == 0) { a.root_stats[4 * c + 2 * rep] = so.iters; a.root_stats[4 * c + 2 * rep + 1] = so.ls; }
       }
@@ -588,13 +729,13 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
         const unsigned bits = (sg == 0) ? full_bits : mask_bits_u8<CPL>(ch, co, a.part_masks + (size_t)(sg - 1) * nq);
 #pragma unroll
         for (int m = 0; m < CPL; m++) q0[m] = q[m];
-        so = solve<CPL, NB, SPL>(ch, co, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
+        so = solve<CPL, NB, SPL>(ch, co, H, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
 #pragma unroll
         for (int m = 0; m < CPL; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];
         bad |= so.bad;
         if (a.iters && lane == 0) { a.iters[sidx + sg] = so.iters; a.ls_evals[sidx + sg] = so.ls; }
         // replace_qs: kinematics normalises the quaternions; the last stage's FK also yields the frame outputs
-        if (sg < a.P) normalize_qpos<CPL, NBF>(ch, co, q);
+        if (sg < a.P) normalize_qpos<CPL>(ch, co, q);
       }
       const size_t fi = (size_t)c * a.F + f;
       full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
@@ -622,6 +763,8 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
   coords_init<CPL>(ch, co, a.lb, a.ub);
   Sites<SPL> st;
   sites_init<SPL>(ch, st, a.site_pos);
+  Hot<NB> H;
+  hot_init<NB>(H, T.act, lane);
   const int nq = T.nq, K = T.K, nb = T.nbody;
   const int wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + wib; b < a.B; b += gridDim.x * wpb) {
@@ -641,7 +784,10 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
       sites_load_kp<SPL>(st, a.kp + (size_t)b * 3 * K);
       sites_mask_u8<SPL>(st, a.kp_mask);
       const unsigned bits = mask_bits_u8<CPL>(ch, co, a.q_mask);
-      const float loss = eval_point<CPL, NB, SPL>(ch, co, q, q0, bits, st, a.out_b != nullptr, g);
+      FkState<NB> S;
+      SiteVals<SPL> sv;
+      const float loss = eval_fwd<CPL, NB, SPL>(ch, co, H, q, q0, bits, st, S, sv);
+      if (a.out_b) eval_bwd<CPL, NB, SPL>(ch, co, H, bits, st, S, sv, g);
       if (lane == 0) a.out_a[b] = loss;
       if (a.out_b) {
 #pragma unroll
@@ -653,7 +799,7 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
       sites_mask_u8<SPL>(st, a.kp_mask);
       const unsigned bits = mask_bits_u8<CPL>(ch, co, a.q_mask);
       float x[CPL];
-      const SolveOut so = solve<CPL, NB, SPL>(ch, co, q, bits, st, a.tol, a.maxiter, a.maxls, x);
+      const SolveOut so = solve<CPL, NB, SPL>(ch, co, H, q, bits, st, a.tol, a.maxiter, a.maxls, x);
 #pragma unroll
       for (int m = 0; m < CPL; m++)
         if (co.valid[m]) a.out_a[(size_t)b * nq + lane + 32 * m] = x[m];
@@ -665,16 +811,15 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
       for (int m = 0; m < CPL; m++)
         if (co.valid[m]) ch.qbuf[lane + 32 * m] = q[m];
       __syncwarp();
-      V3 P[NB];
-      Q4 Q[NB];
-      fk_set<NB, false>(ch, T.act, P, Q, nullptr);
+      FkState<NB> S;
+      fk_hot<NB, false>(ch, H, S);
       float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < SPL; i++) {
+        V3 p;
+        Q4 qb;
+        gather_pose<NB>(ch, S, st.k[i] >= 0 ? st.eact[i] : 0, p, qb);
         if (st.k[i] >= 0) {
-          const float *o = ch.PQ + 7 * st.eact[i];
-          const V3 p = lds3(o);
-          const Q4 qb = lds4(o + 3);
           const V3 z = mk3(st.kp[i].x - p.x, st.kp[i].y - p.y, st.kp[i].z - p.z);
           // math.quat_to_mat
           const float ww = qb.w * qb.w, xx = qb.x * qb.x, yy = qb.y * qb.y, zz = qb.z * qb.z;
