@@ -180,6 +180,19 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
     if (m.jnt_type[j] == STACB_JNT_BALL) qadr.push_back(m.jnt_qposadr[j]);
   }
   T.nquat = (int)qadr.size();
+  // primary free joint (handled warp-uniformly by the hot path) and the rare-joint flag
+  T.free_e = -1; T.free_adr = 0; T.free_sa = 0; T.free_se = 0; T.any_other = 0;
+  for (size_t e = 0; e < act.size(); e++) {
+    const int *r = rec_a.data() + e * REC;
+    for (int jj = 0; jj < r[R_NJNT]; jj++) {
+      const int *jr = r + R_JNT + J_STRIDE * jj;
+      if (jr[J_TYPE] == STACB_JNT_FREE && T.free_e < 0 && jj == 0) {
+        T.free_e = (int)e; T.free_adr = jr[J_ADR]; T.free_sa = jr[J_SA]; T.free_se = jr[J_SE];
+      } else if (jr[J_TYPE] != STACB_JNT_HINGE) {
+        T.any_other = 1;
+      }
+    }
+  }
   if ((rc = upload(t, qadr, &T.quat_adr))) {
     stacb_tree_destroy(t);
     return rc;

@@ -38,6 +38,8 @@ struct DevTree {
   const int *site_efull;  // [K] by sorted position: full-set index of the site's body
   int nqp, pqn, npre;     // per-chain shared memory: qbuf[nqp] gbuf[nqp] PQ[pqn*7] Ipre[npre*6]
   int nquat;              // free / ball joints of the whole model
+  int free_e, free_adr, free_sa, free_se;  // primary free joint: active-set element (-1 if none), qpos address, site range
+  int any_other;          // some active joint is neither a hinge nor the primary free joint (ball / slide / extra free)
   const int *quat_adr;    // [nquat] qpos address of each quaternion
 };
 
@@ -98,16 +100,30 @@ struct Hot {
   BodyConst bc[NB];
   int anc[NB][RMAX];
   bool on[NB];
+  bool hinge[NB][JMAX];  // slot holds a hinge joint
+  bool other[NB][JMAX];  // slot holds a joint handled by the rare (divergent) path
+  int hadr[NB][JMAX];    // qpos address of the hinge (0 when the slot is not a hinge: always a valid address)
+  bool pfree[NB];        // this body carries the primary free joint
 };
 
 template <int NB>
-__device__ __forceinline__ void hot_init(Hot<NB> &H, const DevSet &S, int lane) {
+__device__ __forceinline__ void hot_init(Hot<NB> &H, const DevTree &T, int lane) {
+  const DevSet &S = T.act;
 #pragma unroll
   for (int i = 0; i < NB; i++) {
     const int e = lane + 32 * i;
     H.on[i] = e < S.n;
     load_body(H.bc[i], S.rec + (size_t)(H.on[i] ? e : 0) * REC);
-    if (!H.on[i]) H.bc[i].nj = 0;
+    if (!H.on[i]) { H.bc[i].nj = 0; H.bc[i].parent = -1; }
+    H.pfree[i] = H.on[i] && e == T.free_e;
+#pragma unroll
+    for (int jj = 0; jj < JMAX; jj++) {
+      const bool has = jj < H.bc[i].nj;
+      H.hinge[i][jj] = has && H.bc[i].jtype[jj] == STACB_JNT_HINGE;
+      H.other[i][jj] = has && !H.hinge[i][jj] && !(H.pfree[i] && jj == 0);
+      H.hadr[i][jj] = H.hinge[i][jj] ? H.bc[i].jadr[jj] : 0;
+      if (!H.hinge[i][jj]) { H.bc[i].jref[jj] = 0.f; }
+    }
 #pragma unroll
     for (int r = 0; r < RMAX; r++) H.anc[i][r] = (H.on[i] && r < S.rounds) ? __ldg(S.anc + r * S.n + e) : -1;
   }
@@ -126,6 +142,7 @@ struct FkState {
   V3 P[NB];
   Q4 Q[NB];
   Keep<NB> keep;
+  float fd;  // divisor of the primary free joint's quaternion normalisation (uniform across the warp)
 };
 
 // MJX smooth.kinematics per-body step, evaluated in the parent's frame (canonical order).
@@ -176,25 +193,87 @@ __device__ __forceinline__ void fk_local(const BodyConst &b, float *qbuf, V3 &po
   }
 }
 
-// Hot-path FK over the active set: constants from registers; with one body per lane the pointer-jumping
-// rounds exchange poses by warp shuffles, otherwise through the PQ buffer in shared memory.
+__device__ __forceinline__ V3 sel3(bool c, V3 a, V3 b) { return mk3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+__device__ __forceinline__ Q4 sel4(bool c, Q4 a, Q4 b) { return mk4(c ? a.w : b.w, c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+
+// Hot-path FK over the active set. Same arithmetic as fk_local, laid out for the scheduler:
+//  * the primary free joint is normalised by every lane (uniform code, no divergence) and selected by its body's lane;
+//  * the hinge slots are straight-line code applied through selects (a lane without a hinge in a slot computes on
+//    zeros and discards the result), so the three slots and the bookkeeping rotations interleave freely;
+//  * ball / slide / additional free joints take a divergent path that is skipped warp-uniformly when the model has none.
+// With one body per lane the pointer-jumping rounds exchange poses by warp shuffles, otherwise through PQ in shared memory.
 template <int NB, bool KEEP>
 __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkState<NB> &S) {
+  V3 fpos = mk3(0.f, 0.f, 0.f);
+  Q4 fq = mk4(1.f, 0.f, 0.f, 0.f);
+  float fd = 1.f;
+  if (ch.T.free_e >= 0) {  // uniform
+    const int fa = ch.T.free_adr;
+    fpos = lds3(ch.qbuf + fa);
+    fq = normalize4(lds4(ch.qbuf + fa + 3), &fd);
+  }
+  S.fd = fd;
 #pragma unroll
   for (int i = 0; i < NB; i++) {
-    S.P[i] = mk3(0.f, 0.f, 0.f); S.Q[i] = mk4(1.f, 0.f, 0.f, 0.f);
-    if (H.on[i]) fk_local<NB, KEEP>(H.bc[i], ch.qbuf, S.P[i], S.Q[i], &S.keep, i);
+    const BodyConst &b = H.bc[i];
+    V3 pos = sel3(H.pfree[i], fpos, b.pos);
+    Q4 quat = sel4(H.pfree[i], fq, b.quat);
+    if (KEEP) S.keep.fnorm[i] = fd;
+    float sn[JMAX], cs[JMAX];
+#pragma unroll
+    for (int jj = 0; jj < JMAX; jj++) sincos_canon((ch.qbuf[H.hadr[i][jj]] - b.jref[jj]) * 0.5f, &sn[jj], &cs[jj]);
+#pragma unroll
+    for (int jj = 0; jj < JMAX; jj++) {
+      const V3 jpos = b.jpos[jj], jaxis = b.jaxis[jj];
+      const V3 anchor = add3(rotate(jpos, quat), pos);
+      if (KEEP) { S.keep.anchor[i][jj] = anchor; S.keep.axis[i][jj] = rotate(jaxis, quat); }
+      const Q4 qn = qmul(quat, mk4(cs[jj], jaxis.x * sn[jj], jaxis.y * sn[jj], jaxis.z * sn[jj]));
+      const V3 pn = sub3(anchor, rotate(jpos, qn));
+      pos = sel3(H.hinge[i][jj], pn, pos);
+      quat = sel4(H.hinge[i][jj], qn, quat);
+      if (ch.T.any_other) {  // uniform
+        if (H.other[i][jj]) {
+          const int type = b.jtype[jj], adr = b.jadr[jj];
+          if (type == STACB_JNT_FREE) {
+            float d;
+            pos = lds3(ch.qbuf + adr);
+            if (KEEP) { S.keep.anchor[i][jj] = pos; S.keep.axis[i][jj] = mk3(0.f, 0.f, 1.f); }
+            quat = normalize4(lds4(ch.qbuf + adr + 3), &d);
+            ch.qbuf[adr + 3] = quat.w; ch.qbuf[adr + 4] = quat.x; ch.qbuf[adr + 5] = quat.y; ch.qbuf[adr + 6] = quat.z;
+            if (KEEP) S.keep.fnorm[i] = d;
+          } else if (type == STACB_JNT_BALL) {
+            float d;
+            const Q4 ql = normalize4(lds4(ch.qbuf + adr), &d);
+            ch.qbuf[adr] = ql.w; ch.qbuf[adr + 1] = ql.x; ch.qbuf[adr + 2] = ql.y; ch.qbuf[adr + 3] = ql.z;
+            if (KEEP) S.keep.fnorm[i] = d;
+            quat = qmul(quat, ql);
+            pos = sub3(anchor, rotate(jpos, quat));
+          } else {  // slide
+            const V3 axis = rotate(jaxis, quat);
+            const float d = ch.qbuf[adr] - ldf(ch.T.act.rec + (size_t)(ch.lane + 32 * i) * REC + R_JNT + J_STRIDE * jj + J_REF);
+            pos = mk3(fmaf(axis.x, d, pos.x), fmaf(axis.y, d, pos.y), fmaf(axis.z, d, pos.z));
+          }
+        }
+      }
+    }
+    S.P[i] = pos;
+    S.Q[i] = quat;
+    if (H.pfree[i]) {  // MJX writes the normalised quaternion back into qpos
+      const int fa = ch.T.free_adr;
+      ch.qbuf[fa + 3] = fq.w; ch.qbuf[fa + 4] = fq.x; ch.qbuf[fa + 5] = fq.y; ch.qbuf[fa + 6] = fq.z;
+    }
   }
   const int rounds = ch.T.act.rounds;
   if constexpr (NB == 1) {
 #pragma unroll
     for (int r = 0; r < RMAX; r++) {
-      if (r < rounds) {
+      if (r < rounds) {  // uniform
         const int a = H.anc[0][r];
         const int src = (a >= 0) ? a : ch.lane;
         const V3 pa = shfl3(S.P[0], src);
         const Q4 qa = shfl4(S.Q[0], src);
-        if (a >= 0) { S.P[0] = add3(pa, rotate(S.P[0], qa)); S.Q[0] = qmul(qa, S.Q[0]); }
+        S.P[0] = sel3(a >= 0, add3(pa, rotate(S.P[0], qa)), S.P[0]);
+        S.Q[0] = sel4(a >= 0, qmul(qa, S.Q[0]), S.Q[0]);
       }
     }
   } else {
@@ -208,13 +287,11 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
 #pragma unroll
         for (int i = 0; i < NB; i++) {
           const int a = H.anc[i][r];
-          if (a >= 0) {
-            const float *o = ch.PQ + 7 * a;
-            const V3 pa = lds3(o);
-            const Q4 qa = lds4(o + 3);
-            S.P[i] = add3(pa, rotate(S.P[i], qa));
-            S.Q[i] = qmul(qa, S.Q[i]);
-          }
+          const float *o = ch.PQ + 7 * (a >= 0 ? a : 0);
+          const V3 pa = lds3(o);
+          const Q4 qa = lds4(o + 3);
+          S.P[i] = sel3(a >= 0, add3(pa, rotate(S.P[i], qa)), S.P[i]);
+          S.Q[i] = sel4(a >= 0, qmul(qa, S.Q[i]), S.Q[i]);
         }
         __syncwarp();
       }
@@ -408,59 +485,84 @@ __device__ __forceinline__ void wrench_prefix(const Chain &ch, const Sites<SPL> 
   __syncwarp();
 }
 
+__device__ __forceinline__ void wrench_range(const Chain &ch, int sa, int se, V3 &F, V3 &Tq) {
+  // subtree wrench = difference of inclusive prefixes; callers pass se > sa (empty ranges are clamped and discarded)
+  float wr[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    const float hi = ch.Ipre[6 * (se - 1) + c];
+    const float lo = ch.Ipre[6 * (sa > 0 ? sa - 1 : 0) + c];
+    wr[c] = (sa > 0) ? hi - lo : hi;
+  }
+  F = mk3(wr[0], wr[1], wr[2]);
+  Tq = mk3(wr[3], wr[4], wr[5]);
+}
+
+// d loss / d (raw quaternion) of a normalised quaternion acted on by world torque `tau` (left-multiplied rotation)
+__device__ __forceinline__ void quat_grad_left(Q4 qh, V3 tau, float n, float *g4) {
+  Q4 h = qmul(mk4(0.f, tau.x, tau.y, tau.z), qh);
+  h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
+  const float pr = fmaf(qh.z, h.z, fmaf(qh.y, h.y, fmaf(qh.x, h.x, qh.w * h.w)));
+  g4[0] = fmaf(-qh.w, pr, h.w) / n; g4[1] = fmaf(-qh.x, pr, h.x) / n;
+  g4[2] = fmaf(-qh.y, pr, h.y) / n; g4[3] = fmaf(-qh.z, pr, h.z) / n;
+}
+
 // Reverse sweep: each body lane turns the subtree wrench of its joints into d loss / d qpos (into gbuf).
+// Hinges are straight-line code with predicated stores; the primary free joint is evaluated by every lane
+// (uniform) and stored by lane 0; other joint types take a divergent path skipped when the model has none.
 template <int NB>
 __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, const FkState<NB> &S, V3 cref) {
+  if (ch.T.free_e >= 0 && ch.T.free_se > ch.T.free_sa) {  // uniform
+    V3 F, Tq, fp;
+    Q4 fq;
+    wrench_range(ch, ch.T.free_sa, ch.T.free_se, F, Tq);
+    gather_pose<NB>(ch, S, ch.T.free_e, fp, fq);
+    const float fn = S.fd;
+    const V3 Tp = sub3(Tq, cross3(sub3(fp, cref), F));
+    float g4[4];
+    quat_grad_left(fq, Tp, fn, g4);
+    if (ch.lane == 0) {
+      float *g = ch.gbuf + ch.T.free_adr;
+      g[0] = F.x; g[1] = F.y; g[2] = F.z; g[3] = g4[0]; g[4] = g4[1]; g[5] = g4[2]; g[6] = g4[3];
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NB; i++) {
     const BodyConst &b = H.bc[i];
     V3 pp;
     Q4 pq;
     gather_pose<NB>(ch, S, b.parent >= 0 ? b.parent : 0, pp, pq);
+    const bool has_par = b.parent >= 0;
 #pragma unroll
     for (int jj = 0; jj < JMAX; jj++) {
-      if (jj < b.nj) {
-        const int type = b.jtype[jj], adr = b.jadr[jj], sa = b.jsa[jj], se = b.jse[jj];
-        if (se > sa) {
-          float wr[6];
-#pragma unroll
-          for (int c = 0; c < 6; c++) {
-            const float hi = ch.Ipre[6 * (se - 1) + c];
-            wr[c] = (sa > 0) ? hi - ch.Ipre[6 * (sa - 1) + c] : hi;
-          }
-          const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
-          if (type == STACB_JNT_HINGE || type == STACB_JNT_SLIDE || type == STACB_JNT_BALL) {
-            V3 A = S.keep.anchor[i][jj], W = S.keep.axis[i][jj];
-            if (b.parent >= 0) {
-              A = add3(pp, rotate(A, pq));
-              W = rotate(W, pq);
-            }
-            if (type == STACB_JNT_SLIDE) {
-              ch.gbuf[adr] = dot3(W, F);
-            } else {
-              const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
-              if (type == STACB_JNT_HINGE) {
-                ch.gbuf[adr] = dot3(W, Ta);
-              } else {  // ball (must be the last joint of its body)
-                const Q4 qb = S.Q[i];
-                const V3 tl = rotate(Ta, mk4(qb.w, -qb.x, -qb.y, -qb.z));
-                const Q4 ql = lds4(ch.qbuf + adr);
-                Q4 h = qmul(ql, mk4(0.f, tl.x, tl.y, tl.z));
-                h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
-                const float pr = fmaf(ql.z, h.z, fmaf(ql.y, h.y, fmaf(ql.x, h.x, ql.w * h.w))), n = S.keep.fnorm[i];
-                ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) / n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) / n;
-                ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) / n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) / n;
-              }
-            }
-          } else {  // free
-            const V3 Tp = sub3(Tq, cross3(sub3(S.P[i], cref), F));
-            ch.gbuf[adr] = F.x; ch.gbuf[adr + 1] = F.y; ch.gbuf[adr + 2] = F.z;
-            const Q4 qh = S.Q[i];
-            Q4 h = qmul(mk4(0.f, Tp.x, Tp.y, Tp.z), qh);
+      const int sa = b.jsa[jj], se = b.jse[jj];
+      const bool live = se > sa;
+      V3 F, Tq;
+      wrench_range(ch, live ? sa : 0, live ? se : 1, F, Tq);
+      const V3 A = sel3(has_par, add3(pp, rotate(S.keep.anchor[i][jj], pq)), S.keep.anchor[i][jj]);
+      const V3 W = sel3(has_par, rotate(S.keep.axis[i][jj], pq), S.keep.axis[i][jj]);
+      const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
+      if (H.hinge[i][jj] && live) ch.gbuf[b.jadr[jj]] = dot3(W, Ta);
+      if (ch.T.any_other) {  // uniform
+        if (H.other[i][jj] && live) {
+          const int type = b.jtype[jj], adr = b.jadr[jj];
+          if (type == STACB_JNT_SLIDE) {
+            ch.gbuf[adr] = dot3(W, F);
+          } else if (type == STACB_JNT_BALL) {  // right-multiplied local rotation; last joint of its body
+            const Q4 qb = S.Q[i];
+            const V3 tl = rotate(Ta, mk4(qb.w, -qb.x, -qb.y, -qb.z));
+            const Q4 ql = lds4(ch.qbuf + adr);
+            Q4 h = qmul(ql, mk4(0.f, tl.x, tl.y, tl.z));
             h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
-            const float pr = fmaf(qh.z, h.z, fmaf(qh.y, h.y, fmaf(qh.x, h.x, qh.w * h.w))), n = S.keep.fnorm[i];
-            ch.gbuf[adr + 3] = fmaf(-qh.w, pr, h.w) / n; ch.gbuf[adr + 4] = fmaf(-qh.x, pr, h.x) / n;
-            ch.gbuf[adr + 5] = fmaf(-qh.y, pr, h.y) / n; ch.gbuf[adr + 6] = fmaf(-qh.z, pr, h.z) / n;
+            const float pr = fmaf(ql.z, h.z, fmaf(ql.y, h.y, fmaf(ql.x, h.x, ql.w * h.w))), n = S.keep.fnorm[i];
+            ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) / n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) / n;
+            ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) / n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) / n;
+          } else {  // an additional free joint
+            const V3 Tp = sub3(Tq, cross3(sub3(S.P[i], cref), F));
+            float g4[4];
+            quat_grad_left(S.Q[i], Tp, S.keep.fnorm[i], g4);
+            float *g = ch.gbuf + adr;
+            g[0] = F.x; g[1] = F.y; g[2] = F.z; g[3] = g4[0]; g[4] = g4[1]; g[5] = g4[2]; g[6] = g4[3];
           }
         }
       }
@@ -513,63 +615,83 @@ __device__ __forceinline__ float lane_dot(const float (&a)[CPL], const float (&b
 
 struct SolveOut { float err; int iters, ls; bool bad; };
 
-// jaxopt 0.8.5 ProjectedGradient.run (ProximalGradient._update_accel/_ls/_error, box projection).
-// The reference evaluates FK again for the gradient at the accepted point (grad(fun)(next_x)); the same
-// values are obtained here from the state of the accepting line-search evaluation.
+// jaxopt 0.8.5 ProjectedGradient.run (ProximalGradient._update_accel/_ls/_error, box projection), written as a
+// two-state machine so the kernel contains ONE forward and ONE reverse evaluation (instruction-cache footprint):
+//   state Y : the point is the FISTA extrapolation y -> loss + gradient, then the first line-search candidate
+//   state LS: the point is a candidate x+ -> loss; rejected: halve the step and retry; accepted: gradient at x+ from
+//             the state of this same evaluation (the reference recomputes FK there: same values), error, next y.
 template <int CPL, int NB, int SPL>
 __device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co, const Hot<NB> &H, const float (&q0)[CPL],
                                           unsigned maskbits, const Sites<SPL> &st, float tol, int maxiter, int maxls, float (&x)[CPL]) {
-  float y[CPL], g[CPL], xn[CPL], d[CPL], gn[CPL];
+  float y[CPL], g[CPL], xn[CPL], d[CPL], gt[CPL];
 #pragma unroll
-  for (int m = 0; m < CPL; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; g[m] = 0.f; gn[m] = 0.f; }
-  float t = 1.0f, step = 1.0f, err = __int_as_float(0x7f800000);
+  for (int m = 0; m < CPL; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; xn[m] = x[m]; g[m] = 0.f; gt[m] = 0.f; }
+  float t = 1.0f, step = 1.0f, stp = 1.0f, fy = 0.f, sq = 0.f, dg = 0.f;
+  int halv = 0;
+  bool in_ls = false;
   SolveOut out;
-  out.iters = 0; out.ls = 0; out.bad = false;
-  if (maxiter <= 0) { out.err = err; return out; }
+  out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
+  if (maxiter <= 0) return out;
   FkState<NB> S;
   SiteVals<SPL> sv;
-  do {
-    const float fy = eval_fwd<CPL, NB, SPL>(ch, co, H, y, q0, maskbits, st, S, sv);
-    eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, g);
-    float stp = step;
-    int halv = 0;
-    for (;;) {
+  for (;;) {
+    float pt[CPL];
 #pragma unroll
-      for (int m = 0; m < CPL; m++) {
-        xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
-        d[m] = xn[m] - y[m];
-      }
-      float sq = lane_dot<CPL>(d, d), dg = lane_dot<CPL>(d, g);
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {  // two interleaved butterflies
-        const float a = __shfl_xor_sync(0xffffffffu, sq, off), b2 = __shfl_xor_sync(0xffffffffu, dg, off);
-        sq = sq + a;
-        dg = dg + b2;
-      }
-      const float fn = eval_fwd<CPL, NB, SPL>(ch, co, H, xn, q0, maskbits, st, S, sv);
+    for (int m = 0; m < CPL; m++) pt[m] = in_ls ? xn[m] : y[m];
+    const float f = eval_fwd<CPL, NB, SPL>(ch, co, H, pt, q0, maskbits, st, S, sv);
+    bool rejected = false;
+    if (in_ls) {
       out.ls++;
-      const float dec = stp * (fn - fy);
+      if (!(f - f == 0.0f)) out.bad = true;
+      const float dec = stp * (f - fy);
       const float cond = fmaf(stp, dg, 0.5f * sq);
-      if (!(fn - fn == 0.0f)) out.bad = true;
-      if (!(dec > cond + 1.1920929e-07f) || halv >= maxls) break;
+      rejected = (dec > cond + 1.1920929e-07f) && (halv < maxls);
+    }
+    if (!rejected) {
+      eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, gt);
+      if (in_ls) {  // accepted x+ = xn: FISTA update, error at x+ (unit-step fixed-point residual)
+        step = (stp <= 1e-6f) ? 1.0f : stp / 0.5f;
+        const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+        const float beta = (t - 1.0f) / tn;
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+          y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
+          d[m] = co.valid[m] ? clipf(xn[m] - gt[m], co.lb[m], co.ub[m]) - xn[m] : 0.f;
+          x[m] = xn[m];
+        }
+        out.err = sqrtf(warp_sum(lane_dot<CPL>(d, d)));
+        t = tn;
+        out.iters++;
+        if (!(out.err > tol && out.iters < maxiter)) break;
+        in_ls = false;
+        continue;
+      }
+      // y was evaluated: start the line search from the carried step size
+      fy = f;
+#pragma unroll
+      for (int m = 0; m < CPL; m++) g[m] = gt[m];
+      stp = step;
+      halv = 0;
+      in_ls = true;
+    } else {
       stp = stp * 0.5f;
       halv++;
     }
-    step = (stp <= 1e-6f) ? 1.0f : stp / 0.5f;
-    const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
-    const float beta = (t - 1.0f) / tn;
+    // next candidate x+ = clip(y - stp g) and the two line-search reductions (interleaved butterflies)
 #pragma unroll
-    for (int m = 0; m < CPL; m++) y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
-    eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, gn);
+    for (int m = 0; m < CPL; m++) {
+      xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      d[m] = xn[m] - y[m];
+    }
+    sq = lane_dot<CPL>(d, d);
+    dg = lane_dot<CPL>(d, g);
 #pragma unroll
-    for (int m = 0; m < CPL; m++) d[m] = co.valid[m] ? clipf(xn[m] - gn[m], co.lb[m], co.ub[m]) - xn[m] : 0.f;
-    err = sqrtf(warp_sum(lane_dot<CPL>(d, d)));
-#pragma unroll
-    for (int m = 0; m < CPL; m++) x[m] = xn[m];
-    t = tn;
-    out.iters++;
-  } while (err > tol && out.iters < maxiter);
-  out.err = err;
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float a = __shfl_xor_sync(0xffffffffu, sq, off), b2 = __shfl_xor_sync(0xffffffffu, dg, off);
+      sq = sq + a;
+      dg = dg + b2;
+    }
+  }
   return out;
 }
 
@@ -679,13 +801,16 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
   Sites<SPL> st;
   sites_init<SPL>(ch, st, a.site_pos);
   Hot<NB> H;
-  hot_init<NB>(H, T.act, lane);
+  hot_init<NB>(H, T, lane);
   const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P;
   const unsigned full_bits = mask_bits_u8<CPL>(ch, co, nullptr);
   unsigned root_bits = 0;
 #pragma unroll
   for (int m = 0; m < CPL; m++)
     if (co.valid[m] && lane + 32 * m < a.root_dims) root_bits |= 1u << m;
+  const int n_root = a.do_root ? 2 : 0;                 // two root solves on frame 0 (compute_stac.py:64-98)
+  const int n_pose = (a.do_root == 2) ? 0 : a.F;        // do_root == 2: root optimisation only
+  const int n_stage = n_root + n_pose * S1;             // every stage is one FISTA solve: ONE call site below
 
   for (;;) {
     int c = 0;
@@ -700,47 +825,43 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
     for (int m = 0; m < CPL; m++) q[m] = co.valid[m] ? a.qpos_io[(size_t)c * nq + lane + 32 * m] : 0.f;
     bool bad = false;
     const float *kpc = a.kp + (size_t)c * a.F * 3 * K;
-    if (a.do_root) {
-      sites_load_kp<SPL>(st, kpc);
-      sites_mask_kp<SPL>(st, a.trunk_kps);
-      for (int rep = 0; rep < 2; rep++) {
+    for (int sidx = 0; sidx < n_stage; sidx++) {
+      const bool is_root = sidx < n_root;
+      const int f = is_root ? 0 : (sidx - n_root) / S1;   // frame
+      const int sg = is_root ? 0 : (sidx - n_root) % S1;  // 0: whole body, 1..P: INDIVIDUAL_PART_OPTIMIZATION masks
+      unsigned bits;
+      if (is_root) {
+        if (sidx == 0) { sites_load_kp<SPL>(st, kpc); sites_mask_kp<SPL>(st, a.trunk_kps); }
+        bits = root_bits;
+      } else {
+        if (sg == 0) { sites_load_kp<SPL>(st, kpc + (size_t)f * 3 * K); if (f == 0) sites_mask_kp<SPL>(st, nullptr); }
+        bits = (sg == 0) ? full_bits : mask_bits_u8<CPL>(ch, co, a.part_masks + (size_t)(sg - 1) * nq);
+      }
 #pragma unroll
-        for (int m = 0; m < CPL; m++) {
-          q0[m] = q[m];
-          const int i = lane + 32 * m;
-          if (i < 3) q0[m] = kpc[3 * a.root_kp_idx + i];
-        }
-        const SolveOut so = solve<CPL, NB, SPL>(ch, co, H, q0, root_bits, st, a.tol, a.maxiter, a.maxls, x);
+      for (int m = 0; m < CPL; m++) {
+        q0[m] = q[m];
+        const int i = lane + 32 * m;
+        if (is_root && i < 3) q0[m] = kpc[3 * a.root_kp_idx + i];  // re-seed the root translation from the root keypoint
+      }
+      const SolveOut so = solve<CPL, NB, SPL>(ch, co, H, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
 #pragma unroll
-        for (int m = 0; m < CPL; m++) q[m] = ((root_bits >> m) & 1u) ? x[m] : q0[m];
+      for (int m = 0; m < CPL; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];  // utils.make_qs
+      bad |= so.bad;
+      if (is_root) {
+        if (a.root_stats && lane == 0) { a.root_stats[4 * c + 2 * sidx] = so.iters; a.root_stats[4 * c + 2 * sidx + 1] = so.ls; }
         normalize_qpos<CPL>(ch, co, q);
-        bad |= so.bad;
-        if (a.root_stats && lane == 0) { a.root_stats[4 * c + 2 * rep] = so.iters; a.root_stats[4 * c + 2 * rep + 1] = so.ls; }
-      }
-    }
-    sites_mask_kp<SPL>(st, nullptr);
-    const int n_pose = (a.do_root == 2) ? 0 : a.F;  // do_root == 2: root optimisation only
-    for (int f = 0; f < n_pose; f++) {
-      sites_load_kp<SPL>(st, kpc + (size_t)f * 3 * K);
-      SolveOut so;
-      const size_t sidx = ((size_t)c * a.F + f) * S1;
-      // stage 0: whole body; stages 1..P: INDIVIDUAL_PART_OPTIMIZATION masks (compute_stac.py:216-250)
-      for (int sg = 0; sg <= a.P; sg++) {
-        const unsigned bits = (sg == 0) ? full_bits : mask_bits_u8<CPL>(ch, co, a.part_masks + (size_t)(sg - 1) * nq);
-#pragma unroll
-        for (int m = 0; m < CPL; m++) q0[m] = q[m];
-        so = solve<CPL, NB, SPL>(ch, co, H, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
-#pragma unroll
-        for (int m = 0; m < CPL; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];
-        bad |= so.bad;
-        if (a.iters && lane == 0) { a.iters[sidx + sg] = so.iters; a.ls_evals[sidx + sg] = so.ls; }
+      } else {
+        const size_t fi = (size_t)c * a.F + f;
+        if (a.iters && lane == 0) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
         // replace_qs: kinematics normalises the quaternions; the last stage's FK also yields the frame outputs
-        if (sg < a.P) normalize_qpos<CPL>(ch, co, q);
+        if (sg < a.P) {
+          normalize_qpos<CPL>(ch, co, q);
+        } else {
+          full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
+                                      a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
+          if (a.err && lane == 0) a.err[fi] = so.err;
+        }
       }
-      const size_t fi = (size_t)c * a.F + f;
-      full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
-                                  a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
-      if (a.err && lane == 0) a.err[fi] = so.err;
     }
 #pragma unroll
     for (int m = 0; m < CPL; m++)
@@ -764,7 +885,7 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
   Sites<SPL> st;
   sites_init<SPL>(ch, st, a.site_pos);
   Hot<NB> H;
-  hot_init<NB>(H, T.act, lane);
+  hot_init<NB>(H, T, lane);
   const int nq = T.nq, K = T.K, nb = T.nbody;
   const int wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + wib; b < a.B; b += gridDim.x * wpb) {
