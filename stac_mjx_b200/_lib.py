@@ -18,6 +18,7 @@ SYMBOLS = (
     "stacb_pose_clips",
     "stacb_m_stats",
     "stacb_fma_peak",
+    "stacb_set_mode",
     "stacb_last_error",
     "stacb_version",
 )
@@ -75,6 +76,7 @@ def lib() -> C.CDLL:
         )
         L.stacb_m_stats.argtypes = [vp] * 6 + [i32, vp]
         L.stacb_fma_peak.argtypes = [vp, i32, i32, i32, vp]
+        L.stacb_set_mode.argtypes = [i32]
         L.stacb_last_error.restype = C.c_char_p
         L.stacb_version.restype = i32
         _lib = L

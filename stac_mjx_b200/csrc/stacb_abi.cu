@@ -217,7 +217,7 @@ extern "C" int stacb_tree_smem_per_chain(const stacb_tree *t) { return t ? chain
 
 namespace stacb {
 #define X(c, n, f, p)                                                                                                   \
-  cudaError_t launch_pose_##c##_##n##_##f##_##p(const DevTree &, const PoseArgs &, int, int, size_t, cudaStream_t);     \
+  cudaError_t launch_pose_##c##_##n##_##f##_##p(const DevTree &, const PoseArgs &, int, int, size_t, int, cudaStream_t);     \
   cudaError_t launch_batch_##c##_##n##_##f##_##p(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t);
 STACB_VARIANTS(X)
 #undef X
@@ -227,18 +227,25 @@ static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl) {
   return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl;
 }
 
+static int g_force_mode = -1;  // -1 auto, 0 one warp per chain (throughput), 1 four warps per chain (latency)
+
 static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
   CUDA_TRY(cudaSetDevice(t->device));
   CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(int), s));
-  // few chains: one warp per CTA so every chain gets an SM to itself; many: 4 warps per CTA
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
-  const int wpb = (a.C <= 2 * sms) ? 1 : 4;
-  const int grid = std::min((a.C + wpb - 1) / wpb, sms * 16);
-  const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
+  // Few chains: latency mode, one CTA of four cooperating warps per chain (speculative line search, see solve4).
+  // Many chains: throughput mode, one warp per chain, four chains per CTA.
+  const size_t chain_bytes = (size_t)chain_smem_floats(t->T) * 4;
+  const size_t coop_bytes = 4 * chain_bytes + ((size_t)t->T.nqp + 8) * 4;
+  int coop = (a.C <= 2 * sms) && coop_bytes <= 200 * 1024;
+  if (g_force_mode >= 0) coop = g_force_mode && coop_bytes <= 200 * 1024;
+  const int wpb = 4;
+  const int grid = coop ? std::min(a.C, sms * 8) : std::min((a.C + wpb - 1) / wpb, sms * 16);
+  const size_t smem = coop ? coop_bytes : wpb * chain_bytes;
   if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
 #define X(c, n, f, p) \
-  if (fits(t, c, n, f, p)) { CUDA_TRY(launch_pose_##c##_##n##_##f##_##p(t->T, a, grid, 32 * wpb, smem, s)); return STACB_OK; }
+  if (fits(t, c, n, f, p)) { CUDA_TRY(launch_pose_##c##_##n##_##f##_##p(t->T, a, grid, 32 * wpb, smem, coop, s)); return STACB_OK; }
   STACB_VARIANTS(X)
 #undef X
   return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
@@ -321,6 +328,12 @@ extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, vo
   if (!out || blocks <= 0 || threads <= 0 || iters < 0) return fail(STACB_E_INVALID, "stacb_fma_peak: bad argument");
   fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(out, iters);
   CUDA_TRY(cudaGetLastError());
+  return STACB_OK;
+}
+
+extern "C" int stacb_set_mode(int mode) {
+  if (mode < -1 || mode > 1) return fail(STACB_E_INVALID, "stacb_set_mode: mode must be -1 (auto), 0 (throughput) or 1 (latency)");
+  g_force_mode = mode;
   return STACB_OK;
 }
 

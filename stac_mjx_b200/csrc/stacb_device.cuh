@@ -695,6 +695,124 @@ __device__ __forceinline__ SolveOut solve(const Chain &ch, const Coords<CPL> &co
   return out;
 }
 
+// ------------------------------------------------------------------------------------------
+// Latency mode: four warps (one per SM sub-partition) cooperate on ONE chain.
+// Per FISTA iteration the reference's sequence  f(x+_0), f(x+_1), ..., grad f(x+), f(y'), grad f(y')  is
+// evaluated speculatively in parallel:
+//   warp 0: f at candidate x+_a (step s)        warp 2: f at y'(x+_a) = x+_a + beta (x+_a - x)
+//   warp 1: f at candidate x+_b (step s/2)      warp 3: f at y'(x+_b)
+// then the warp of the first accepted candidate k computes grad f(x+_k) (stopping criterion) while warp 2+k
+// computes grad f(y') for the next iteration.  Every evaluation is the same arithmetic as in the one-warp solver,
+// and the accepted candidate is chosen exactly as the sequential line search would, so results are bit-identical;
+// only the critical path per iteration shrinks from 3 forward + 2 reverse evaluations to 1 + 1.
+// ------------------------------------------------------------------------------------------
+struct Coop {
+  float *g;            // [nqp] broadcast of grad f(y')
+  volatile float *sc;  // [0..1] accept flags, [2] err, [3] f(y'), [4] sticky non-finite flag
+  int w;               // warp role 0..3
+};
+
+template <int CPL, int NB, int SPL>
+__device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, const Coords<CPL> &co, const Hot<NB> &H, const float (&q0)[CPL],
+                                           unsigned maskbits, const Sites<SPL> &st, float tol, int maxiter, int maxls, float (&x)[CPL]) {
+  float y[CPL], g[CPL], gt[CPL], xa[CPL], xb[CPL], pt[CPL], d[CPL];
+#pragma unroll
+  for (int m = 0; m < CPL; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; g[m] = 0.f; gt[m] = 0.f; }
+  float t = 1.0f, step = 1.0f;
+  SolveOut out;
+  out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
+  if (maxiter <= 0) return out;
+  FkState<NB> S;
+  SiteVals<SPL> sv;
+  const int w = cp.w;
+  // f(y0), grad f(y0): every warp computes them (identical values, no broadcast needed)
+  float fy = eval_fwd<CPL, NB, SPL>(ch, co, H, y, q0, maskbits, st, S, sv);
+  eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, g);
+  int base = 0;
+  float stp_a = step;
+  for (;;) {
+    const float stp_b = stp_a * 0.5f;
+    const float stp_m = (w & 1) ? stp_b : stp_a;
+    const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+    const float beta = (t - 1.0f) / tn;
+    float sq = 0.f, dg = 0.f;
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+      xa[m] = co.valid[m] ? clipf(fmaf(-stp_a, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      xb[m] = co.valid[m] ? clipf(fmaf(-stp_b, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      const float mine = (w & 1) ? xb[m] : xa[m];
+      pt[m] = (w < 2) ? mine : fmaf(beta, mine - x[m], mine);
+      d[m] = mine - y[m];
+    }
+    if (w < 2) {
+      sq = lane_dot<CPL>(d, d);
+      dg = lane_dot<CPL>(d, g);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const float a = __shfl_xor_sync(0xffffffffu, sq, off), b2 = __shfl_xor_sync(0xffffffffu, dg, off);
+        sq = sq + a;
+        dg = dg + b2;
+      }
+    }
+    const float f = eval_fwd<CPL, NB, SPL>(ch, co, H, pt, q0, maskbits, st, S, sv);
+    if (w < 2) {
+      const float dec = stp_m * (f - fy);
+      const float cond = fmaf(stp_m, dg, 0.5f * sq);
+      const bool rejected = (dec > cond + 1.1920929e-07f) && (base + w < maxls);
+      if (ch.lane == 0) {
+        cp.sc[w] = rejected ? 0.f : 1.f;
+        if (!(f - f == 0.0f)) cp.sc[4] = 1.f;
+      }
+    }
+    __syncthreads();
+    const bool a0 = cp.sc[0] != 0.f, a1 = cp.sc[1] != 0.f;
+    if (!a0 && !a1) {  // both candidates rejected: next pair of step sizes
+      base += 2;
+      stp_a = stp_b * 0.5f;
+      __syncthreads();
+      continue;
+    }
+    const int k = a0 ? 0 : 1;
+    out.ls += base + k + 1;  // evaluations the sequential line search performs
+    const float stp_k = k ? stp_b : stp_a;
+    if (w == k || w == 2 + k) {
+      eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, gt);
+      if (w == k) {  // gradient at x+ -> unit-step fixed-point residual
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+          const float xk = k ? xb[m] : xa[m];
+          d[m] = co.valid[m] ? clipf(xk - gt[m], co.lb[m], co.ub[m]) - xk : 0.f;
+        }
+        const float err = sqrtf(warp_sum(lane_dot<CPL>(d, d)));
+        if (ch.lane == 0) cp.sc[2] = err;
+      } else {  // gradient at y' -> next iteration
+#pragma unroll
+        for (int m = 0; m < CPL; m++)
+          if (co.valid[m]) cp.g[ch.lane + 32 * m] = gt[m];
+        if (ch.lane == 0) cp.sc[3] = f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+      const float xk = k ? xb[m] : xa[m];
+      y[m] = fmaf(beta, xk - x[m], xk);
+      x[m] = xk;
+      g[m] = co.valid[m] ? cp.g[ch.lane + 32 * m] : 0.f;
+    }
+    fy = cp.sc[3];
+    out.err = cp.sc[2];
+    t = tn;
+    step = (stp_k <= 1e-6f) ? 1.0f : stp_k / 0.5f;
+    out.iters++;
+    if (!(out.err > tol && out.iters < maxiter)) break;
+    base = 0;
+    stp_a = step;
+  }
+  __syncthreads();
+  return out;
+}
+
 // replace_qs (utils.py:147-169) as far as qpos is concerned: kinematics normalises free / ball
 // quaternions in place. q holds the full qpos vector of the chain.
 template <int CPL>
@@ -791,11 +909,17 @@ struct PoseArgs {
   int *counter;
 };
 
-template <int CPL, int NB, int NBF, int SPL>
+template <int CPL, int NB, int NBF, int SPL, bool COOP>
 __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) {
   extern __shared__ float smem[];
+  __shared__ int s_chain;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   Chain ch(T, smem + (size_t)wib * chain_smem_floats(T), lane);
+  Coop cp;
+  cp.g = smem + (size_t)4 * chain_smem_floats(T);
+  cp.sc = cp.g + T.nqp;
+  cp.w = wib;
+  const bool writer = !COOP || wib == 0;  // latency mode: the four warps hold identical state, warp 0 writes the outputs
   Coords<CPL> co;
   coords_init<CPL>(ch, co, a.lb, a.ub);
   Sites<SPL> st;
@@ -814,8 +938,15 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
 
   for (;;) {
     int c = 0;
-    if (lane == 0) c = atomicAdd(a.counter, 1);
-    c = __shfl_sync(0xffffffffu, c, 0);
+    if (COOP) {
+      if (threadIdx.x == 0) { s_chain = atomicAdd(a.counter, 1); cp.sc[4] = 0.f; }
+      __syncthreads();
+      c = s_chain;
+      __syncthreads();
+    } else {
+      if (lane == 0) c = atomicAdd(a.counter, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+    }
     if (c >= a.C) break;
     for (int m = 0; m < CPL; m++)
       if (co.valid[m]) ch.gbuf[lane + 32 * m] = 0.f;
@@ -843,18 +974,20 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
         const int i = lane + 32 * m;
         if (is_root && i < 3) q0[m] = kpc[3 * a.root_kp_idx + i];  // re-seed the root translation from the root keypoint
       }
-      const SolveOut so = solve<CPL, NB, SPL>(ch, co, H, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
+      SolveOut so;
+      if constexpr (COOP) so = solve4<CPL, NB, SPL>(ch, cp, co, H, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
+      else so = solve<CPL, NB, SPL>(ch, co, H, q0, bits, st, a.tol, a.maxiter, a.maxls, x);
 #pragma unroll
       for (int m = 0; m < CPL; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];  // utils.make_qs
       bad |= so.bad;
       if (is_root) {
-        if (a.root_stats && lane == 0) { a.root_stats[4 * c + 2 * sidx] = so.iters; a.root_stats[4 * c + 2 * sidx + 1] = so.ls; }
+        if (a.root_stats && lane == 0 && writer) { a.root_stats[4 * c + 2 * sidx] = so.iters; a.root_stats[4 * c + 2 * sidx + 1] = so.ls; }
         normalize_qpos<CPL>(ch, co, q);
       } else {
         const size_t fi = (size_t)c * a.F + f;
-        if (a.iters && lane == 0) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
+        if (a.iters && lane == 0 && writer) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
         // replace_qs: kinematics normalises the quaternions; the last stage's FK also yields the frame outputs
-        if (sg < a.P) {
+        if (sg < a.P || !writer) {
           normalize_qpos<CPL>(ch, co, q);
         } else {
           full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
@@ -863,10 +996,13 @@ __global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) 
         }
       }
     }
+    if (COOP) { if (cp.sc[4] != 0.f) bad = true; }
+    if (writer) {
 #pragma unroll
-    for (int m = 0; m < CPL; m++)
-      if (co.valid[m]) a.qpos_io[(size_t)c * nq + lane + 32 * m] = q[m];
-    if (a.status && lane == 0) a.status[c] = bad ? 1 : 0;
+      for (int m = 0; m < CPL; m++)
+        if (co.valid[m]) a.qpos_io[(size_t)c * nq + lane + 32 * m] = q[m];
+      if (a.status && lane == 0) a.status[c] = bad ? 1 : 0;
+    }
   }
 }
 

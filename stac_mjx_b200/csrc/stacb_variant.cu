@@ -9,8 +9,9 @@ namespace stacb {
 #define FN_(prefix, a, b, c, d) prefix##a##_##b##_##c##_##d
 #define FN(prefix, a, b, c, d) FN_(prefix, a, b, c, d)
 
-cudaError_t FN(launch_pose_, V_CPL, V_NB, V_NBF, V_SPL)(const DevTree &T, const PoseArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-  auto k = pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL>;
+cudaError_t FN(launch_pose_, V_CPL, V_NB, V_NBF, V_SPL)(const DevTree &T, const PoseArgs &a, int grid, int block, size_t smem, int coop,
+                                                        cudaStream_t s) {
+  auto k = coop ? pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, true> : pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

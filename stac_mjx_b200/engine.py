@@ -71,6 +71,10 @@ class Engine:
     def empty(self, *shape, dtype=torch.float32) -> torch.Tensor:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    def set_mode(self, mode: int) -> None:
+        """Scheduling of pose_clips: -1 auto, 0 throughput (warp per chain), 1 latency (4 warps per chain)."""
+        _lib.check(self._L.stacb_set_mode(int(mode)), "stacb_set_mode")
+
     @property
     def smem_per_chain(self) -> int:
         return int(self._L.stacb_tree_smem_per_chain(self._h))

@@ -92,6 +92,32 @@ def test_clips_match_golden(name, engine_of):
         assert np.array_equal(o[k], g[f"c32_clip_{k}"]), f"{k} no longer bit-identical to the canonical oracle"
 
 
+@pytest.mark.parametrize("name", ["rodent", "fly_treadmill", "mouse"])
+def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
+    """Four cooperating warps per chain (speculative line search) vs one warp per chain: same bits, same counters."""
+    c = get_case(name)
+    eng = engine_of(c)
+    F = 3 if name == "mouse" else 6
+    kp, _, _ = c.session(5 * F, F, seed=41)
+    kp = kp.reshape(5, F, -1)
+    outs = []
+    try:
+        for mode in (0, 1):
+            eng.set_mode(mode)
+            qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (5, 1)), device=eng.device)
+            o = eng.pose_clips(kp, qio, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
+            outs.append({k: npy(v) for k, v in o.items()} | {"qio": npy(qio)})
+    finally:
+        eng.set_mode(-1)
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    ref = c.oracle(np.float32, 1).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
+                                              nthreads=4, **c.root_kw())  # fmt: skip
+    np.testing.assert_allclose(outs[1]["qpos"], ref["qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_array_equal(outs[1]["iters"], ref["iters"])
+    np.testing.assert_array_equal(outs[1]["ls_evals"], ref["ls_evals"])
+
+
 def test_rodent_clip_against_live_oracle(rodent, engine_of):
     """Fresh seeded inputs (not the committed ones): 3 clips x 12 frames of the rodent, all 6 solves per frame."""
     eng = engine_of(rodent)

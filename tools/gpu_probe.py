@@ -63,6 +63,8 @@ print(" iters equal", np.array_equal(out["iters"].cpu().numpy(), ref["iters"]), 
       "root", out["root_stats"].cpu().numpy()[0], ref["root_stats"][0], "status", out["status"].cpu().numpy())
 
 # timing: 72 clips x 250
+import os
+eng.set_mode(int(os.environ.get('STACB_MODE', '-1')))
 for C in (72, 148, 592):
     kpb, _, _ = synth.synth_session(t, s, C * F, F, seed=7)
     kpd = torch.tensor(kpb.reshape(C, F, -1), device="cuda")
