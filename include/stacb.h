@@ -129,7 +129,8 @@ int stacb_m_stats(const stacb_tree *tree, const float *kp, const float *q, float
 int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream);
 
 /* Scheduling of stacb_pose_clips: -1 auto (default), 0 throughput mode (one warp per clip chain),
- * 1 latency mode (four cooperating warps per chain, speculative line search). Results are bit-identical. */
+ * 1 latency mode (four cooperating warps per chain, speculative line search), 2 dense throughput mode (registers
+ * capped so 16 chains fit per SM; chosen automatically from 16 chains per SM). Results are bit-identical. */
 int stacb_set_mode(int mode);
 
 const char *stacb_last_error(void);

@@ -6,11 +6,12 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -I ../../include ${STACB_NVCC_EXTRA}"
 mkdir -p _obj
-VARIANTS=$(sed -n 's/^#define STACB_VARIANTS(X)//p' stacb_variants.h | sed 's/X(\([0-9]*\), *\([0-9]*\), *\([0-9]*\), *\([0-9]*\))/\1_\2_\3_\4/g')
+rm -f _obj/*.o
+VARIANTS=$(sed -n 's/^#define STACB_VARIANTS(X)//p' stacb_variants.h | sed 's/X(\([0-9]*\), *\([0-9]*\), *\([0-9]*\), *\([0-9]*\), *\([0-9]*\))/\1_\2_\3_\4_\5/g')
 pids=""
 for v in $VARIANTS; do
   set -- $(echo $v | tr '_' ' ')
-  $NVCC $FLAGS -DV_CPL=$1 -DV_NB=$2 -DV_NBF=$3 -DV_SPL=$4 -c stacb_variant.cu -o _obj/variant_$v.o > _obj/variant_$v.log 2>&1 &
+  $NVCC $FLAGS -DV_CPL=$1 -DV_NB=$2 -DV_NBF=$3 -DV_SPL=$4 -DV_JM=$5 -c stacb_variant.cu -o _obj/variant_$v.o > _obj/variant_$v.log 2>&1 &
   pids="$pids $!"
 done
 $NVCC $FLAGS -c stacb_abi.cu -o _obj/abi.o > _obj/abi.log 2>&1 &

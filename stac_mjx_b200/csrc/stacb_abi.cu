@@ -57,7 +57,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct stacb_tree {
   int device;
   DevTree T;
-  int cpl, bpl_act, bpl_full;
+  int cpl, bpl_act, bpl_full, jm_act;
   std::vector<void *> allocs;
   int *counter;
 };
@@ -197,6 +197,8 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
     stacb_tree_destroy(t);
     return rc;
   }
+  t->jm_act = 1;
+  for (size_t e = 0; e < act.size(); e++) t->jm_act = std::max(t->jm_act, rec_a[e * REC + R_NJNT]);
   t->cpl = (m.nq + 31) / 32; t->bpl_act = (T.act.n + 31) / 32; t->bpl_full = (T.full.n + 31) / 32;
   T.nqp = 32 * t->cpl; T.pqn = std::max(T.act.n, T.full.n); T.npre = 32 * T.spl;
   void *cnt = nullptr;
@@ -216,18 +218,18 @@ extern "C" void stacb_tree_destroy(stacb_tree *t) {
 extern "C" int stacb_tree_smem_per_chain(const stacb_tree *t) { return t ? chain_smem_floats(t->T) * 4 : 0; }
 
 namespace stacb {
-#define X(c, n, f, p)                                                                                                   \
-  cudaError_t launch_pose_##c##_##n##_##f##_##p(const DevTree &, const PoseArgs &, int, int, size_t, int, cudaStream_t);     \
-  cudaError_t launch_batch_##c##_##n##_##f##_##p(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t);
+#define X(c, n, f, p, j)                                                                                                    \
+  cudaError_t launch_pose_##c##_##n##_##f##_##p##_##j(const DevTree &, const PoseArgs &, int, int, size_t, int, cudaStream_t); \
+  cudaError_t launch_batch_##c##_##n##_##f##_##p##_##j(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t);
 STACB_VARIANTS(X)
 #undef X
 }  // namespace stacb
 
-static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl) {
-  return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl;
+static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl, int jm) {
+  return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl && t->jm_act <= jm;
 }
 
-static int g_force_mode = -1;  // -1 auto, 0 one warp per chain (throughput), 1 four warps per chain (latency)
+static int g_force_mode = -1;  // -1 auto, 0 throughput, 1 latency (four warps per chain), 2 dense throughput (128 registers)
 
 static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
   CUDA_TRY(cudaSetDevice(t->device));
@@ -238,14 +240,15 @@ static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
   // Many chains: throughput mode, one warp per chain, four chains per CTA.
   const size_t chain_bytes = (size_t)chain_smem_floats(t->T) * 4;
   const size_t coop_bytes = 4 * chain_bytes + ((size_t)t->T.nqp + 8) * 4;
-  int coop = (a.C <= 2 * sms) && coop_bytes <= 200 * 1024;
-  if (g_force_mode >= 0) coop = g_force_mode && coop_bytes <= 200 * 1024;
+  int coop = (a.C <= 2 * sms) ? 1 : (a.C >= 16 * sms ? 2 : 0);
+  if (g_force_mode >= 0) coop = g_force_mode;
+  if (coop == 1 && coop_bytes > 200 * 1024) coop = 0;
   const int wpb = 4;
-  const int grid = coop ? std::min(a.C, sms * 8) : std::min((a.C + wpb - 1) / wpb, sms * 16);
-  const size_t smem = coop ? coop_bytes : wpb * chain_bytes;
+  const int grid = coop == 1 ? std::min(a.C, sms * 8) : std::min((a.C + wpb - 1) / wpb, sms * 16);
+  const size_t smem = coop == 1 ? coop_bytes : wpb * chain_bytes;
   if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
-#define X(c, n, f, p) \
-  if (fits(t, c, n, f, p)) { CUDA_TRY(launch_pose_##c##_##n##_##f##_##p(t->T, a, grid, 32 * wpb, smem, coop, s)); return STACB_OK; }
+#define X(c, n, f, p, j) \
+  if (fits(t, c, n, f, p, j)) { CUDA_TRY(launch_pose_##c##_##n##_##f##_##p##_##j(t->T, a, grid, 32 * wpb, smem, coop, s)); return STACB_OK; }
   STACB_VARIANTS(X)
 #undef X
   return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
@@ -260,8 +263,8 @@ static int run_batch(const stacb_tree *t, const BatchArgs &a, cudaStream_t s) {
   const int grid = std::min((a.B + wpb - 1) / wpb, sms * 16);
   const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
   if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
-#define X(c, n, f, p) \
-  if (fits(t, c, n, f, p)) { CUDA_TRY(launch_batch_##c##_##n##_##f##_##p(t->T, a, grid, 32 * wpb, smem, s)); return STACB_OK; }
+#define X(c, n, f, p, j) \
+  if (fits(t, c, n, f, p, j)) { CUDA_TRY(launch_batch_##c##_##n##_##f##_##p##_##j(t->T, a, grid, 32 * wpb, smem, s)); return STACB_OK; }
   STACB_VARIANTS(X)
 #undef X
   return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
@@ -332,7 +335,7 @@ extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, vo
 }
 
 extern "C" int stacb_set_mode(int mode) {
-  if (mode < -1 || mode > 1) return fail(STACB_E_INVALID, "stacb_set_mode: mode must be -1 (auto), 0 (throughput) or 1 (latency)");
+  if (mode < -1 || mode > 2) return fail(STACB_E_INVALID, "stacb_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency) or 2 (dense throughput)");
   g_force_mode = mode;
   return STACB_OK;
 }

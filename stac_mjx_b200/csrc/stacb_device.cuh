@@ -19,7 +19,11 @@
 
 namespace stacb {
 
-constexpr int JMAX = 3;                     // joints per body handled in place
+constexpr int JMAX = 3;                     // joints per body the descriptor can hold
+#ifndef V_JM
+#define V_JM 3
+#endif
+constexpr int JM = V_JM;                    // joint slots the hot path of this kernel variant processes (<= JMAX)
 constexpr int REC = 10 + 12 * JMAX + 1;     // words per body record (odd stride)
 constexpr int R_POS = 0, R_QUAT = 3, R_NJNT = 7, R_PARENT = 8, R_BODY = 9, R_JNT = 10;
 constexpr int J_TYPE = 0, J_ADR = 1, J_POS = 2, J_AXIS = 5, J_REF = 8, J_SA = 9, J_SE = 10, J_STRIDE = 12;
@@ -100,9 +104,9 @@ struct Hot {
   BodyConst bc[NB];
   int anc[NB][RMAX];
   bool on[NB];
-  bool hinge[NB][JMAX];  // slot holds a hinge joint
-  bool other[NB][JMAX];  // slot holds a joint handled by the rare (divergent) path
-  int hadr[NB][JMAX];    // qpos address of the hinge (0 when the slot is not a hinge: always a valid address)
+  bool hinge[NB][JM];  // slot holds a hinge joint
+  bool other[NB][JM];  // slot holds a joint handled by the rare (divergent) path
+  int hadr[NB][JM];    // qpos address of the hinge (0 when the slot is not a hinge: always a valid address)
   bool pfree[NB];        // this body carries the primary free joint
 };
 
@@ -117,7 +121,7 @@ __device__ __forceinline__ void hot_init(Hot<NB> &H, const DevTree &T, int lane)
     if (!H.on[i]) { H.bc[i].nj = 0; H.bc[i].parent = -1; }
     H.pfree[i] = H.on[i] && e == T.free_e;
 #pragma unroll
-    for (int jj = 0; jj < JMAX; jj++) {
+    for (int jj = 0; jj < JM; jj++) {
       const bool has = jj < H.bc[i].nj;
       H.hinge[i][jj] = has && H.bc[i].jtype[jj] == STACB_JNT_HINGE;
       H.other[i][jj] = has && !H.hinge[i][jj] && !(H.pfree[i] && jj == 0);
@@ -219,11 +223,11 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
     V3 pos = sel3(H.pfree[i], fpos, b.pos);
     Q4 quat = sel4(H.pfree[i], fq, b.quat);
     if (KEEP) S.keep.fnorm[i] = fd;
-    float sn[JMAX], cs[JMAX];
+    float sn[JM], cs[JM];
 #pragma unroll
-    for (int jj = 0; jj < JMAX; jj++) sincos_canon((ch.qbuf[H.hadr[i][jj]] - b.jref[jj]) * 0.5f, &sn[jj], &cs[jj]);
+    for (int jj = 0; jj < JM; jj++) sincos_canon((ch.qbuf[H.hadr[i][jj]] - b.jref[jj]) * 0.5f, &sn[jj], &cs[jj]);
 #pragma unroll
-    for (int jj = 0; jj < JMAX; jj++) {
+    for (int jj = 0; jj < JM; jj++) {
       const V3 jpos = b.jpos[jj], jaxis = b.jaxis[jj];
       const V3 anchor = add3(rotate(jpos, quat), pos);
       if (KEEP) { S.keep.anchor[i][jj] = anchor; S.keep.axis[i][jj] = rotate(jaxis, quat); }
@@ -534,7 +538,7 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
     gather_pose<NB>(ch, S, b.parent >= 0 ? b.parent : 0, pp, pq);
     const bool has_par = b.parent >= 0;
 #pragma unroll
-    for (int jj = 0; jj < JMAX; jj++) {
+    for (int jj = 0; jj < JM; jj++) {
       const int sa = b.jsa[jj], se = b.jse[jj];
       const bool live = se > sa;
       V3 F, Tq;
@@ -909,8 +913,11 @@ struct PoseArgs {
   int *counter;
 };
 
-template <int CPL, int NB, int NBF, int SPL, bool COOP>
-__global__ void __launch_bounds__(128) pose_clips_kernel(DevTree T, PoseArgs a) {
+// MODE 0: throughput (one warp per chain, 4 chains per CTA); MODE 1: latency (4 cooperating warps per chain);
+// MODE 2: dense throughput (registers capped at 128 so 16 warps fit per SM; pays off from ~16 chains per SM).
+template <int CPL, int NB, int NBF, int SPL, int MODE>
+__global__ void __launch_bounds__(128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevTree T, PoseArgs a) {
+  constexpr bool COOP = MODE == 1;
   extern __shared__ float smem[];
   __shared__ int s_chain;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
