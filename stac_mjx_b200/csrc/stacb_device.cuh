@@ -102,7 +102,7 @@ constexpr int RMAX = 8;  // pointer-jumping rounds kept in registers (tree depth
 template <int NB>
 struct Hot {
   BodyConst bc[NB];
-  int anc[NB][RMAX];
+  unsigned long long anc_lo[NB], anc_hi[NB];  // ancestor at distance 2^r, 16 bits per round (0xffff = none)
   bool on[NB];
   bool hinge[NB][JM];  // slot holds a hinge joint
   bool other[NB][JM];  // slot holds a joint handled by the rare (divergent) path
@@ -128,9 +128,22 @@ __device__ __forceinline__ void hot_init(Hot<NB> &H, const DevTree &T, int lane)
       H.hadr[i][jj] = H.hinge[i][jj] ? H.bc[i].jadr[jj] : 0;
       if (!H.hinge[i][jj]) { H.bc[i].jref[jj] = 0.f; }
     }
+    H.anc_lo[i] = ~0ull; H.anc_hi[i] = ~0ull;
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) H.anc[i][r] = (H.on[i] && r < S.rounds) ? __ldg(S.anc + r * S.n + e) : -1;
+    for (int r = 0; r < RMAX; r++) {
+      const int a = (H.on[i] && r < S.rounds) ? __ldg(S.anc + r * S.n + e) : -1;
+      const unsigned long long v = (unsigned long long)(a & 0xffff) << (16 * (r & 3));
+      const unsigned long long mask = ~(0xffffull << (16 * (r & 3)));
+      if (r < 4) H.anc_lo[i] = (H.anc_lo[i] & mask) | v; else H.anc_hi[i] = (H.anc_hi[i] & mask) | v;
+    }
   }
+}
+
+template <int NB>
+__device__ __forceinline__ int hot_anc(const Hot<NB> &H, int i, int r) {
+  const unsigned long long p = (r < 4) ? H.anc_lo[i] : H.anc_hi[i];
+  const int a = (int)((p >> (16 * (r & 3))) & 0xffffull);
+  return a == 0xffff ? -1 : a;
 }
 
 // Per-lane results of the local phase that the reverse sweep needs.
@@ -235,7 +248,7 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
       const V3 pn = sub3(anchor, rotate(jpos, qn));
       pos = sel3(H.hinge[i][jj], pn, pos);
       quat = sel4(H.hinge[i][jj], qn, quat);
-      if (ch.T.any_other) {  // uniform
+      if (__builtin_expect(ch.T.any_other != 0, 0)) {  // uniform, rare
         if (H.other[i][jj]) {
           const int type = b.jtype[jj], adr = b.jadr[jj];
           if (type == STACB_JNT_FREE) {
@@ -269,36 +282,32 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
   }
   const int rounds = ch.T.act.rounds;
   if constexpr (NB == 1) {
-#pragma unroll
-    for (int r = 0; r < RMAX; r++) {
-      if (r < rounds) {  // uniform
-        const int a = H.anc[0][r];
-        const int src = (a >= 0) ? a : ch.lane;
-        const V3 pa = shfl3(S.P[0], src);
-        const Q4 qa = shfl4(S.Q[0], src);
-        S.P[0] = sel3(a >= 0, add3(pa, rotate(S.P[0], qa)), S.P[0]);
-        S.Q[0] = sel4(a >= 0, qmul(qa, S.Q[0]), S.Q[0]);
-      }
+#pragma unroll 1
+    for (int r = 0; r < rounds; r++) {
+      const int a = hot_anc<NB>(H, 0, r);
+      const int src = (a >= 0) ? a : ch.lane;
+      const V3 pa = shfl3(S.P[0], src);
+      const Q4 qa = shfl4(S.Q[0], src);
+      S.P[0] = sel3(a >= 0, add3(pa, rotate(S.P[0], qa)), S.P[0]);
+      S.Q[0] = sel4(a >= 0, qmul(qa, S.Q[0]), S.Q[0]);
     }
   } else {
+#pragma unroll 1
+    for (int r = 0; r < rounds; r++) {
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) {
-      if (r < rounds) {
+      for (int i = 0; i < NB; i++)
+        if (H.on[i]) sts7(ch.PQ + 7 * (ch.lane + 32 * i), S.P[i], S.Q[i]);
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NB; i++)
-          if (H.on[i]) sts7(ch.PQ + 7 * (ch.lane + 32 * i), S.P[i], S.Q[i]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < NB; i++) {
-          const int a = H.anc[i][r];
-          const float *o = ch.PQ + 7 * (a >= 0 ? a : 0);
-          const V3 pa = lds3(o);
-          const Q4 qa = lds4(o + 3);
-          S.P[i] = sel3(a >= 0, add3(pa, rotate(S.P[i], qa)), S.P[i]);
-          S.Q[i] = sel4(a >= 0, qmul(qa, S.Q[i]), S.Q[i]);
-        }
-        __syncwarp();
+      for (int i = 0; i < NB; i++) {
+        const int a = hot_anc<NB>(H, i, r);
+        const float *o = ch.PQ + 7 * (a >= 0 ? a : 0);
+        const V3 pa = lds3(o);
+        const Q4 qa = lds4(o + 3);
+        S.P[i] = sel3(a >= 0, add3(pa, rotate(S.P[i], qa)), S.P[i]);
+        S.Q[i] = sel4(a >= 0, qmul(qa, S.Q[i]), S.Q[i]);
       }
+      __syncwarp();
     }
 #pragma unroll
     for (int i = 0; i < NB; i++)
@@ -547,7 +556,7 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
       const V3 W = sel3(has_par, rotate(S.keep.axis[i][jj], pq), S.keep.axis[i][jj]);
       const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
       if (H.hinge[i][jj] && live) ch.gbuf[b.jadr[jj]] = dot3(W, Ta);
-      if (ch.T.any_other) {  // uniform
+      if (__builtin_expect(ch.T.any_other != 0, 0)) {  // uniform, rare
         if (H.other[i][jj] && live) {
           const int type = b.jtype[jj], adr = b.jadr[jj];
           if (type == STACB_JNT_SLIDE) {
