@@ -71,3 +71,66 @@ def load_stac_data(file_path: str | Path):
             qpos=f["qpos"][()], qvel=f["qvel"][()], xpos=f["xpos"][()], xquat=f["xquat"][()],
         )  # fmt: skip
     return config, data
+
+
+def load_data(cfg, base_path: Path | None = None):
+    """Load mocap, order keypoints like ``KEYPOINT_MODEL_PAIRS``, scale, flatten (reference ``io.py:39-98``).
+
+    Returns ``(kp_data [n_frames, 3K] float32, sorted keypoint names)``; the flattened layout is keypoint-major,
+    xyz-minor -- the wire layout of every kernel entry point.
+    """
+    base_path = Path.cwd() if base_path is None else Path(base_path)
+    file_path = base_path / cfg.stac.data_path
+    if file_path.suffix == ".mat":
+        data, kp_names = load_dannce(str(file_path), names_filename=cfg.model.get("KP_NAMES_LABEL3D_PATH", None))
+    elif file_path.suffix == ".nwb":
+        data, kp_names = load_nwb(file_path)
+    elif file_path.suffix == ".h5":
+        data, kp_names = load_h5(file_path)
+    else:
+        raise ValueError("Unsupported file extension. Please provide a .mat, .nwb, or .h5 file.")
+    kp_names = kp_names or cfg.model.get("KP_NAMES", None)
+    if kp_names is None:
+        raise ValueError(
+            "Keypoint names not provided. Please provide an ordered list of keypoint names corresponding to the keypoint data order."
+        )
+    if len(kp_names) != data.shape[2]:
+        raise ValueError(
+            f"Number of keypoint names ({len(kp_names)}) is not the same as the number of keypoints in data ({data.shape[2]})"
+        )
+    model_inds = [list(kp_names).index(src) for src in cfg.model.KEYPOINT_MODEL_PAIRS.keys()]
+    sorted_names = [kp_names[i] for i in model_inds]
+    data = (np.asarray(data) * cfg.model.MOCAP_SCALE_FACTOR)[:, :, model_inds]
+    data = np.transpose(data, (0, 2, 1)).reshape(data.shape[0], -1)
+    return np.ascontiguousarray(data, dtype=np.float32), sorted_names
+
+
+def load_dannce(filename, names_filename=None):
+    """DANNCE ``.mat``: ``pred`` [frames, xyz, keypoints] in millimetres (reference ``io.py:101-124``)."""
+    import scipy.io as spio
+
+    names = None
+    if names_filename is not None:
+        mat = spio.loadmat(names_filename)
+        names = [item[0] for sub in mat["joint_names"] for item in sub]
+    return np.asarray(spio.loadmat(filename)["pred"]), names
+
+
+def load_nwb(filename):
+    """NWB pose estimation: [frames, xyz, keypoints] + node names (reference ``io.py:127-148``)."""
+    from pynwb import NWBHDF5IO
+
+    with NWBHDF5IO(filename, mode="r", load_namespaces=True) as f:
+        pose = f.read().processing["behavior"]["PoseEstimation"]
+        names = pose.nodes[:].tolist()
+        data = np.stack([pose[n].data[:] for n in names], axis=-1)
+    return data, names
+
+
+def load_h5(filename):
+    """``tracks`` dataset [frames, 1, keypoints, xyz] -> [frames, xyz, keypoints] (reference ``io.py:151-171``)."""
+    import h5py
+
+    with h5py.File(filename, "r") as f:
+        data = np.array(f["tracks"][()])
+    return np.transpose(np.squeeze(data, axis=1), (0, 2, 1)), None

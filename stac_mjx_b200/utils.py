@@ -70,3 +70,38 @@ def handle_edge_effects(ik_only_data, n_frames_per_clip: int):
     for k in ("qpos", "kp_data", "xpos", "xquat", "marker_sites"):
         setattr(ik_only_data, k, f(getattr(ik_only_data, k)))
     return ik_only_data
+
+
+def _quat_mul(a, b):
+    return np.stack(
+        [
+            a[..., 0] * b[..., 0] - a[..., 1] * b[..., 1] - a[..., 2] * b[..., 2] - a[..., 3] * b[..., 3],
+            a[..., 0] * b[..., 1] + a[..., 1] * b[..., 0] + a[..., 2] * b[..., 3] - a[..., 3] * b[..., 2],
+            a[..., 0] * b[..., 2] - a[..., 1] * b[..., 3] + a[..., 2] * b[..., 0] + a[..., 3] * b[..., 1],
+            a[..., 0] * b[..., 3] + a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1] + a[..., 3] * b[..., 0],
+        ],
+        axis=-1,
+    )
+
+
+def compute_velocity_from_kinematics(qpos_trajectory, dt: float, freejoint: bool = True, max_qvel: float = 20.0):
+    """Finite-difference qvel of one continuous clip (reference ``utils.py:302-347``), vectorised over frames.
+
+    The last frame is repeated (zero velocity there); with a free joint the angular velocity is the axis-angle of
+    ``conj(q_t) * q_{t+1}`` divided by dt and only the joint velocities are clipped to ``max_qvel``.
+    """
+    q = np.asarray(qpos_trajectory, dtype=np.float32)
+    q = np.concatenate([q, q[-1:]], axis=0)
+    if not freejoint:
+        return np.clip((q[1:] - q[:-1]) / dt, -max_qvel, max_qvel)
+    joints = (q[1:, 7:] - q[:-1, 7:]) / dt
+    trans = (q[1:, :3] - q[:-1, :3]) / dt
+    conj = q[:-1, 3:7] * np.array([1.0, -1.0, -1.0, -1.0], dtype=np.float32)
+    diff = _quat_mul(conj, q[1:, 3:7])
+    diff = diff / np.linalg.norm(diff, axis=-1, keepdims=True)
+    angle = 2.0 * np.arccos(np.clip(diff[:, 0], -1.0, 1.0))
+    half_sin = np.sin(angle / 2.0)
+    wrapped = (angle + np.pi) % (2.0 * np.pi) - np.pi
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gyro = np.where((angle < 1e-10)[:, None], 0.0, diff[:, 1:4] / half_sin[:, None] * wrapped[:, None]) / dt
+    return np.concatenate([trans, gyro, np.clip(joints, -max_qvel, max_qvel)], axis=1).astype(np.float32)

@@ -274,3 +274,18 @@ def test_full_size_properties(rodent, engine_of):
     np.testing.assert_allclose(a["qpos"][ci], ref["qpos"][0], atol=QPOS_TOL, rtol=0)
     np.testing.assert_allclose(a["sites"][ci], ref["sites"][0], atol=MARKER_TOL, rtol=0)
     np.testing.assert_array_equal(a["iters"][ci], ref["iters"][0])
+
+
+def test_real_mocap_clip_matches_golden(rodent, engine_of):
+    """BASELINE config 1: 250 frames of the reference's real rat23 recording, root optimisation + 6 solves per frame."""
+    g = golden("rodent_real250")
+    eng = engine_of(rodent)
+    s = rodent.setup
+    qio = torch.tensor(rodent.tree.qpos0.astype(np.float32)[None], device=eng.device)
+    out = eng.pose_clips(g["kp"][None], qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+    np.testing.assert_array_equal(npy(out["iters"])[0], g["c32_iters"])
+    np.testing.assert_array_equal(npy(out["root_stats"])[0], g["c32_root_stats"])
+    np.testing.assert_allclose(npy(out["qpos"])[0], g["c32_qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(npy(out["sites"])[0], g["c32_sites"], atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(npy(out["err"])[0], g["c32_err"], rtol=REL_TOL)
+    assert np.array_equal(npy(out["qpos"])[0], g["c32_qpos"])

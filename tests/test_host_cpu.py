@@ -176,3 +176,47 @@ def test_edge_effect_crossfade_shapes():
                     names_qpos=[], names_xpos=[], kp_names=[])  # fmt: skip
     out = utils.handle_edge_effects(d, F)
     assert out.qpos.shape == (n_clip * F, 5) and out.xpos.shape == (n_clip * F, 2, 3)
+
+
+def test_velocity_from_kinematics():
+    # reference tests/unit/test_utils_math.py: constant joint ramp without a free joint, and a pure z rotation with one
+    dt = 0.1
+    q = np.stack([np.linspace(0, 1, 5), np.linspace(0, -2, 5)], axis=1)
+    v = utils.compute_velocity_from_kinematics(q, dt, freejoint=False)
+    np.testing.assert_allclose(v[:-1], np.tile([2.5, -5.0], (4, 1)), rtol=1e-5)
+    np.testing.assert_allclose(v[-1], 0.0)
+    ang = np.linspace(0, 0.4, 5)
+    qf = np.zeros((5, 9))
+    qf[:, 0] = np.linspace(0, 1, 5)
+    qf[:, 3], qf[:, 6] = np.cos(ang / 2), np.sin(ang / 2)
+    qf[:, 8] = 100.0 * np.arange(5)
+    v = utils.compute_velocity_from_kinematics(qf, dt)
+    assert v.shape == (5, 8)
+    np.testing.assert_allclose(v[:-1, 0], 2.5, rtol=1e-5)
+    np.testing.assert_allclose(v[:-1, 5], 1.0, rtol=1e-4)  # 0.1 rad per 0.1 s about z
+    np.testing.assert_allclose(v[:-1, 3:5], 0.0, atol=1e-5)
+    assert (v[:-1, 7] == 20.0).all()  # joint velocities clipped, root velocities not
+
+
+def test_real_mocap_fixture_is_what_load_data_produces(tmp_path):
+    """io.load_data on a DANNCE-style .mat: order by KEYPOINT_MODEL_PAIRS, scale, flatten keypoint-major (io.py:39-98)."""
+    import scipy.io as spio
+
+    from conftest import ROOT, get_case
+    from stac_mjx_b200.config import Cfg
+
+    c = get_case("rodent")
+    g = np.load(ROOT / "tests" / "golden" / "rodent_real250.npz")
+    # rebuild a [frames, xyz, keypoints] millimetre array in the mocap's own KP_NAMES order and round-trip it
+    names_model = c.kp_names
+    names_mocap = list(c.cfg.model.KP_NAMES)
+    kp = g["kp"][:20].reshape(20, len(names_model), 3)
+    pred = np.zeros((20, 3, len(names_mocap)))
+    for k, n in enumerate(names_model):
+        pred[:, :, names_mocap.index(n)] = kp[:, k, :] / c.cfg.model.MOCAP_SCALE_FACTOR
+    spio.savemat(tmp_path / "m.mat", {"pred": pred})
+    cfg = Cfg(c.cfg.to_dict())
+    cfg.stac.data_path = "m.mat"
+    out, names = io.load_data(cfg, base_path=tmp_path)
+    assert names == names_model and out.shape == (20, 69) and out.dtype == np.float32
+    np.testing.assert_allclose(out, g["kp"][:20], rtol=1e-6, atol=1e-9)

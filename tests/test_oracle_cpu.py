@@ -228,3 +228,13 @@ def test_noise_floor_is_reported(rodent, capsys):
         print(f"\n[noise floor] rodent f32(canonical) vs f64(mjx order): qpos max {dq.max():.2e} median {np.median(dq):.2e} rad;"
               f" marker max {ds.max():.2e} m")  # fmt: skip
     assert ds.max() < 5e-3
+
+
+def test_oracle_reproduces_real_mocap_clip(rodent):
+    """BASELINE config 1: the first frames of the reference's real rat23 recording (committed, tools/make_real_fixture.py)."""
+    g = np.load(ROOT / "tests" / "golden" / "rodent_real250.npz")
+    s = rodent.setup
+    n = 25
+    r = rodent.oracle(np.float32, 1).pose_clips(g["kp"][None, :n], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+    np.testing.assert_array_equal(r["qpos"][0], g["c32_qpos"][:n])
+    np.testing.assert_array_equal(r["iters"][0], g["c32_iters"][:n])
