@@ -114,7 +114,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} rat23 q-phase, bounded CPU sample of {int(frames_per_step)} frames per step", "clip_frames": args.clip},
+        "config": {"workload": f"{args.model}.xml rat23 synthetic {args.frames}-frame session per GPU in {args.clip}-frame clips "
+                               f"({args.frames // args.clip} independent chains), root optimisation + {1 + setup.indiv_parts.shape[0]} FISTA solves per frame, "
+                               f"FTOL {float(cfg.model.FTOL):g}, N_ITER_Q {int(cfg.model.N_ITER_Q)}",
+                   "sample": f"each step times a bounded sample of {int(frames_per_step)} frames of that workload on the host CPU",
+                   "clip_frames": args.clip},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -255,6 +259,16 @@ def run_ours(args):
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed ncu capture
+    tfile = ROOT / "profiles" / "traffic_r1d_bench_launch.csv"
+    if tfile.exists() and args.model == "rodent" and C * F == 18000:
+        try:
+            import csv
+
+            vals = {r[12]: float(r[14]) for r in csv.reader(tfile.open()) if len(r) > 14 and r[12].startswith("dram__bytes")}
+            traffic = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+        except Exception:
+            traffic = None
     h2d = kp_host.numel() * 4
     d2h = sum(int(v.numel()) * v.element_size() for v in host_out.values())
 
@@ -277,7 +291,7 @@ def run_ours(args):
             },
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                "traffic": None,
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic_r1d_bench_launch.csv; outputs mostly still in L2)",
                 "note": "FP32 CUDA-core bound path (no tensor-core or HBM-bound kernel exists on it): algorithmic flops (stac_mjx_b200/flops.py, "
                         "SURVEY 8(d)) of one launch / CUDA-event duration; peak = FFMA throughput measured in this run by stacb_fma_peak "
                         "(not in MEASURED_PEAKS.json, which holds HBM and bf16 tensor peaks only)",
