@@ -193,18 +193,26 @@ def run_ours(args):
         qio = q0.clone()
         return eng.pose_clips(kp_dev, qio, setup.initial_offsets, setup.lb, setup.ub, setup.indiv_parts, out=out, **kw)
 
-    host_out = {}
+    # e2e: the call a user makes -- Stac.ik_only(kp_data, offsets) on HOST arrays: pinned staging + H2D of the step's
+    # keypoints, the fused kernel, D2H of every result into host memory and the reference's StacData packing
+    import contextlib
+    import io as _io
+
+    from stac_mjx_b200.config import Cfg
+    from stac_mjx_b200.stac import Stac
+
+    ecfg = Cfg(cfg.to_dict())
+    ecfg.stac.n_frames_per_clip, ecfg.stac.continuous = F, False
+    kp_names = list(cfg.model.KEYPOINT_MODEL_PAIRS.keys())
+    with contextlib.redirect_stdout(_io.StringIO()):
+        stac = Stac(None, ecfg, kp_names, tree=tree, device=local)
+    e2e_bytes = {}
 
     def step_e2e():
-        # the call a user makes, with HOST buffers: H2D of the step's keypoints, the fused kernel, D2H of every result
-        kd = kp_host.to(dev, non_blocking=True)
-        qio = q0.clone()
-        o = eng.pose_clips(kd, qio, setup.initial_offsets, setup.lb, setup.ub, setup.indiv_parts, out=out, **kw)
-        for k in ("qpos", "xpos", "xquat", "sites", "err"):
-            if k not in host_out:
-                host_out[k] = torch.empty(o[k].shape, dtype=o[k].dtype).pin_memory()
-            host_out[k].copy_(o[k], non_blocking=True)
-        return o
+        with contextlib.redirect_stdout(_io.StringIO()):
+            d = stac.ik_only(kp, setup.initial_offsets)
+        e2e_bytes["d2h"] = d.qpos.nbytes + d.xpos.nbytes + d.xquat.nbytes + d.marker_sites.nbytes + C * F * 4
+        return d
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -270,7 +278,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     h2d = kp_host.numel() * 4
-    d2h = sum(int(v.numel()) * v.element_size() for v in host_out.values())
+    d2h = int(e2e_bytes.get("d2h", 0))
 
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:

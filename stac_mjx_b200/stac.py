@@ -116,44 +116,72 @@ class Stac:
 
     # ------------------------------------------------------------------
     def ik_only(self, kp_data, offsets) -> io.StacData:
-        """Inverse kinematics with fixed offsets over independent clips (reference ``stac.py:356-454``)."""
+        """Inverse kinematics with fixed offsets over independent clips (reference ``stac.py:356-454``).
+
+        The reference vmaps ``root_optimization`` and ``pose_optimization`` over clips; here the whole phase is ONE
+        fused launch (``stacb_pose_clips`` with ``do_root=1``) on this rank's block of clips.  Outputs are produced
+        directly in the reference's packed layout (``_package_data(batched=True)``, ``stac.py:483-486``): qpos / xpos /
+        xquat clip-major -- which is the kernel's native layout -- and marker_sites frame-major (transposed on the GPU).
+        """
         kp_data = np.asarray(kp_data, dtype=np.float32)
         batched_kp_data = utils.batch_kp_data(kp_data, self.cfg.stac.n_frames_per_clip, continuous=self.cfg.stac.continuous)
         eng = self._engine
-        C = batched_kp_data.shape[0]
+        C, F = batched_kp_data.shape[:2]
         rank, ws = parallel.world()
         lo, hi = parallel.shard_range(C, rank, ws)
-        mjx_model, data0 = self._load(np.asarray(offsets, dtype=np.float32))
-        # pinned staging -> device (the step's H2D copy)
-        host = torch.from_numpy(np.ascontiguousarray(batched_kp_data[lo:hi]))
-        kp_dev = host.pin_memory().to(eng.device, non_blocking=True) if host.numel() else host.to(eng.device)
-        mjx_data = stac_core.StacState(qpos=data0.qpos.repeat(hi - lo, 1))
+        offsets = np.asarray(offsets, dtype=np.float32)
+        site_pos = eng.f32(offsets, (eng.K, 3))
+        # pinned staging -> device: the step's H2D copy
+        stage = self._pinned("kp_in", (hi - lo, F, batched_kp_data.shape[2]), torch.float32)
+        stage.copy_(torch.from_numpy(np.ascontiguousarray(batched_kp_data[lo:hi])))
+        kp_dev = stage.to(eng.device, non_blocking=True)
+        qio = eng.f32(self._mj_model.qpos0).repeat(hi - lo, 1).contiguous()
+        has_root = self._root_kp_idx != -1 and not self._fixed
         if self._root_kp_idx == -1:
             print("Missing or invalid ROOT_OPTIMIZATION_KEYPOINT, skipping root_optimization()")
-        elif not self._fixed:
-            mjx_data = compute_stac.root_optimization(
-                self.stac_core_obj, mjx_model, mjx_data, kp_dev, self._root_kp_idx, self._lb, self._ub,
-                self._body_site_idxs, self._trunk_kps,
-            )  # fmt: skip
-        else:
+        elif self._fixed:
             print("ROOT_OPTIMIZATION_KEYPOINT specified but model has fixed root, skipping root_optimization()")
-        mjx_data, qposes, xposes, xquats, marker_sites, frame_time, frame_error = compute_stac.pose_optimization(
-            self.stac_core_obj, mjx_model, mjx_data, kp_dev, self._lb, self._ub, self._body_site_idxs, self._indiv_parts
-        )
-        self.last_stats = mjx_data.solver_stats
-        if ws > 1:  # hand every rank the complete result, clip-major like the single-process run
-            qposes = parallel.allgather_blocks(qposes.contiguous(), C)
-            xposes = parallel.allgather_blocks(xposes.transpose(0, 1).contiguous(), C).transpose(0, 1)
-            xquats = parallel.allgather_blocks(xquats.transpose(0, 1).contiguous(), C).transpose(0, 1)
-            marker_sites = parallel.allgather_blocks(marker_sites.transpose(0, 1).contiguous(), C).transpose(0, 1)
-            frame_error = parallel.allgather_blocks(frame_error.transpose(0, 1).contiguous(), C).transpose(0, 1)
-        _, mean, std = self._get_error_stats(frame_error)
+        q = self.stac_core_obj.q_solver
+        out = eng.pose_clips(
+            kp_dev, qio, site_pos, self._lb, self._ub, self._indiv_parts, do_root=1 if has_root else 0,
+            root_kp_idx=max(self._root_kp_idx, 0), trunk_kps=self._trunk_kps, root_dims=4 if self._slidejoint else 7,
+            tol=q.tol, maxiter=q.maxiter, maxls=q.maxls,
+        )  # fmt: skip
+        self.last_stats = {"iters": out["iters"], "ls_evals": out["ls_evals"], "status": out["status"], "root_stats": out["root_stats"]}
+        res = {k: out[k] for k in ("qpos", "xpos", "xquat", "sites", "err")}
+        if ws > 1:  # hand every rank the complete result (blocks are contiguous in the clip-major layout)
+            res = {k: parallel.allgather_blocks(v.contiguous(), C) for k, v in res.items()}
+        nb, K = eng.nbody, eng.K
+        dev = {
+            "qpos": res["qpos"].reshape(C * F, eng.nq),
+            "xpos": res["xpos"].reshape(C * F, nb, 3),
+            "xquat": res["xquat"].reshape(C * F, nb, 4),
+            "marker_sites": res["sites"].transpose(0, 1).reshape(C * F, K, 3),  # frame-major interleave (stac.py:486)
+            "err": res["err"],
+        }
+        host = {}
+        for k, v in dev.items():  # the step's D2H read, through pinned buffers
+            buf = self._pinned("out_" + k, tuple(v.shape), v.dtype)
+            buf.copy_(v, non_blocking=True)
+            host[k] = buf
+        torch.cuda.synchronize(eng.device)
+        _, mean, std = self._get_error_stats(host["err"].numpy())
         print(f"Mean: {mean}")
         print(f"Standard deviation: {std}")
-        return self._package_data(
-            mjx_model, qposes.cpu().numpy(), xposes.cpu().numpy(), xquats.cpu().numpy(), marker_sites.cpu().numpy(),
-            batched_kp_data, batched=True,
+        return io.StacData(
+            qpos=host["qpos"].numpy().copy(), xpos=host["xpos"].numpy().copy(), xquat=host["xquat"].numpy().copy(),
+            marker_sites=host["marker_sites"].numpy().copy(), offsets=np.array(offsets), names_qpos=self._part_names,
+            names_xpos=self._body_names, kp_data=batched_kp_data.reshape(-1, batched_kp_data.shape[-1]), kp_names=self._kp_names,
         )  # fmt: skip
+
+    def _pinned(self, key: str, shape, dtype) -> torch.Tensor:
+        """Reusable page-locked host buffer (allocating pinned memory per call would dominate small sessions)."""
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        buf = cache.get(key)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(tuple(shape), dtype=dtype).pin_memory() if int(np.prod(shape)) else torch.empty(tuple(shape), dtype=dtype)
+            cache[key] = buf
+        return buf
 
     # ------------------------------------------------------------------
     def _package_data(self, mjx_model, qposes, xposes, xquats, marker_sites, kp_data, batched: bool = False) -> io.StacData:
