@@ -275,6 +275,7 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
     }
     S.P[i] = pos;
     S.Q[i] = quat;
+    if (ch.T.free_e >= 0) __syncwarp();  // every lane has read the raw quaternion before its owner overwrites it
     if (H.pfree[i]) {  // MJX writes the normalised quaternion back into qpos
       const int fa = ch.T.free_adr;
       ch.qbuf[fa + 3] = fq.w; ch.qbuf[fa + 4] = fq.x; ch.qbuf[fa + 5] = fq.y; ch.qbuf[fa + 6] = fq.z;
@@ -1012,7 +1013,7 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevT
         }
       }
     }
-    if (COOP) { if (cp.sc[4] != 0.f) bad = true; }
+    if (COOP && threadIdx.x == 0) { if (cp.sc[4] != 0.f) bad = true; }  // thread 0 clears, reads and reports the flag: program order
     if (writer) {
 #pragma unroll
       for (int m = 0; m < CPL; m++)
