@@ -289,3 +289,53 @@ def test_real_mocap_clip_matches_golden(rodent, engine_of):
     np.testing.assert_allclose(npy(out["sites"])[0], g["c32_sites"], atol=MARKER_TOL, rtol=0)
     np.testing.assert_allclose(npy(out["err"])[0], g["c32_err"], rtol=REL_TOL)
     assert np.array_equal(npy(out["qpos"])[0], g["c32_qpos"])
+
+
+def test_all_joint_types_on_gpu():
+    """The rare-joint paths of the kernels (ball, slide, a second free joint, 3 joints on one body) against the oracle."""
+    from mixed_model import mixed_tree, random_qpos
+    from oracle.oracle import Oracle
+    from stac_mjx_b200.engine import Engine
+
+    t, site_idxs, lb, ub = mixed_tree()
+    sb = t.site_bodyid[site_idxs]
+    off = t.site_pos[site_idxs].astype(np.float32)
+    K = len(sb)
+    eng = Engine(t, sb, 0)
+    o = Oracle(t, sb, np.float32, 1)
+    rng = np.random.default_rng(1)
+    q = random_qpos(t, rng, 6).astype(np.float32)
+    got = [npy(x) for x in eng.fk(q, off)]
+    kp = np.stack([o.fk(q[(i + 1) % 6], off)[3].reshape(-1) for i in range(6)]).astype(np.float32) + 0.005
+    for i in range(6):
+        ref = o.fk(q[i], off)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a[i], b)
+    qm, km = np.ones(t.nq, bool), np.ones(3 * K, bool)
+    L, G = [npy(x) for x in eng.loss_grad(q, q, kp, qm, km, off)]
+    for i in range(6):
+        l, g = o.loss_grad(q[i], q[i], qm, kp[i], km, off)
+        assert float(l) == float(L[i])
+        np.testing.assert_array_equal(G[i], g)
+    # masked solve (only the arm / wrist DOFs) and a full clip with root optimisation, all three scheduling modes
+    part = np.zeros(t.nq, bool)
+    part[7:16] = True
+    p, e, it, ls = [npy(x) for x in eng.q_opt(q[:3], kp[:3], part, km, off, lb, ub, 1e-5, maxiter=80)]
+    for i in range(3):
+        po, eo, ito, lso = o.q_opt(q[i], lb, ub, part, kp[i], km, off, 1e-5, maxiter=80)
+        assert (it[i], ls[i]) == (ito, lso)
+        np.testing.assert_array_equal(p[i], po)
+    kpc = kp.reshape(2, 3, -1)
+    kw = dict(do_root=1, root_kp_idx=0, trunk_kps=np.ones(K, bool), tol=1e-5, maxiter=60)
+    ref = o.pose_clips(kpc, t.qpos0, off, lb, ub, part[None], **kw)
+    try:
+        for mode in (0, 1, 2):
+            eng.set_mode(mode)
+            qio = torch.tensor(np.tile(t.qpos0.astype(np.float32), (2, 1)), device=eng.device)
+            out = eng.pose_clips(kpc, qio, off, lb, ub, part[None], **kw)
+            np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
+            for k in ("qpos", "xpos", "xquat", "sites", "err"):
+                np.testing.assert_array_equal(npy(out[k]), ref[k])
+    finally:
+        eng.set_mode(-1)
+    np.testing.assert_allclose(np.linalg.norm(ref["qpos"][..., 3:7], axis=-1), 1.0, atol=1e-6)

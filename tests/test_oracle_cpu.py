@@ -238,3 +238,32 @@ def test_oracle_reproduces_real_mocap_clip(rodent):
     r = rodent.oracle(np.float32, 1).pose_clips(g["kp"][None, :n], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
     np.testing.assert_array_equal(r["qpos"][0], g["c32_qpos"][:n])
     np.testing.assert_array_equal(r["iters"][0], g["c32_iters"][:n])
+
+
+def test_all_joint_types_gradient_and_orders():
+    """free + extra free + hinge + slide + ball joints, 2-3 joints per body: analytic gradient vs reverse-mode autodiff,
+    canonical vs MJX order, un-normalised quaternions included."""
+    from mixed_model import mixed_tree, random_qpos
+
+    t, site_idxs, lb, ub = mixed_tree()
+    sb = t.site_bodyid[site_idxs]
+    off = t.site_pos[site_idxs]
+    rng = np.random.default_rng(0)
+    q = random_qpos(t, rng, 4)
+    T = TorchModel(t, sb)
+    o0, o1 = Oracle(t, sb, np.float64, 0), Oracle(t, sb, np.float64, 1)
+    qm, km = np.ones(t.nq, bool), np.ones(3 * len(sb), bool)
+    for i in range(4):
+        kp = o0.fk(q[(i + 1) % 4], off)[3].reshape(-1) + 0.01
+        L, G = T.loss_grad(q[i], q[i], qm, kp, km, off)
+        for o in (o0, o1):
+            l, g = o.loss_grad(q[i], q[i], qm, kp, km, off)
+            assert abs(float(l) - L) < 1e-12 * max(1.0, L)
+            np.testing.assert_allclose(g, G, atol=2e-8 * max(1.0, np.abs(G).max()))
+        a, b = o0.fk(q[i], off), o1.fk(q[i], off)
+        for x, y in zip(a, b):
+            np.testing.assert_allclose(x, y, atol=1e-13)
+        np.testing.assert_allclose(np.linalg.norm(a[0][3:7]), 1.0, atol=1e-12)  # quaternions normalised in the returned qpos
+    f32 = Oracle(t, sb, np.float32, 1)
+    p, e, it, ls = f32.q_opt(q[0], lb, ub, qm, kp, km, off, 1e-5, maxiter=60)
+    assert it > 3 and np.isfinite(p).all()
