@@ -115,6 +115,65 @@ class Stac:
         )
 
     # ------------------------------------------------------------------
+    def fit_offsets_clip_split(self, kp_data, n_frames_per_clip: int | None = None) -> io.StacData:
+        """OPT-IN deviation from the reference schedule: the fit's q-phase over independent clips.
+
+        The reference runs the q-phase of ``fit_offsets`` as ONE warm-started chain over all ``n_fit_frames``
+        (``stac.py:298-342``), which cannot use more than one GPU (or more than one SM).  Here the fit frames are cut into
+        clips of ``n_frames_per_clip`` exactly like ``ik_only`` does (root optimisation on each clip's first frame in the
+        first pass, warm start carried per clip from pass to pass), the clips are block-partitioned over ranks, and the
+        m-phase statistics of every rank's sampled frames are all-reduced.  With a single clip and a single rank this is
+        the reference schedule.  Results differ from `fit_offsets` only through the different warm starts.
+        """
+        kp_data = np.asarray(kp_data, dtype=np.float32)
+        F = int(n_frames_per_clip or self.cfg.stac.n_frames_per_clip)
+        clips = utils.batch_kp_data(kp_data, F, continuous=False)
+        C = clips.shape[0]
+        eng, q = self._engine, self.stac_core_obj.q_solver
+        rank, ws = parallel.world()
+        lo, hi = parallel.shard_range(C, rank, ws)
+        kp_dev = eng.f32(np.ascontiguousarray(clips[lo:hi]))
+        kp_flat = kp_dev.reshape(-1, kp_dev.shape[-1])
+        self._offsets = np.array(self._setup.initial_offsets)
+        qio = eng.f32(self._mj_model.qpos0).repeat(hi - lo, 1).contiguous()
+        has_root = self._root_kp_idx != -1 and not self._fixed
+        tidx_all = self.time_indices
+        if tidx_all is None:
+            tidx_all = compute_stac.sample_time_indices(C * F, int(self.cfg.model.N_SAMPLE_FRAMES))
+        tidx_all = np.sort(np.asarray(tidx_all))
+        mine = tidx_all[(tidx_all >= lo * F) & (tidx_all < hi * F)] - lo * F  # this rank's share of the frame sample
+        mjx_model = stac_core.StacModel(engine=eng, site_pos=eng.f32(self._offsets, (eng.K, 3)))
+        out = None
+        for n_iter in range(self.cfg.model.N_ITERS + 1):
+            last = n_iter == self.cfg.model.N_ITERS
+            print("Final pose optimization" if last else f"Calibration iteration: {n_iter + 1}/{self.cfg.model.N_ITERS}", flush=True)
+            out = eng.pose_clips(
+                kp_dev, qio, mjx_model.site_pos, self._lb, self._ub, self._indiv_parts, do_root=1 if (has_root and n_iter == 0) else 0,
+                root_kp_idx=max(self._root_kp_idx, 0), trunk_kps=self._trunk_kps, root_dims=4 if self._slidejoint else 7,
+                tol=q.tol, maxiter=q.maxiter, maxls=q.maxls,
+            )  # fmt: skip
+            if last:
+                break
+            idx = torch.as_tensor(mine, device=eng.device, dtype=torch.long)
+            res = self.stac_core_obj.m_opt(
+                mjx_model, None, kp_flat[idx], out["qpos"].reshape(-1, eng.nq)[idx], self._offsets, self._is_regularized,
+                self.cfg.model.M_REG_COEF, self._body_site_idxs, reduce_fn=parallel.allreduce_m_stats if ws > 1 else None,
+            )  # fmt: skip
+            print(f"Final residual error of {float(res.error)}")
+            mjx_model = mjx_model.replace(site_pos=res.params)
+            self._offsets = res.params.cpu().numpy()
+        self.last_stats = {"iters": out["iters"], "ls_evals": out["ls_evals"], "status": out["status"]}
+        res = {k: out[k] for k in ("qpos", "xpos", "xquat", "sites")}
+        if ws > 1:
+            res = {k: parallel.allgather_blocks(v.contiguous(), C) for k, v in res.items()}
+        flat = lambda t: t.reshape((C * F,) + tuple(t.shape[2:])).cpu().numpy()
+        return io.StacData(
+            qpos=flat(res["qpos"]), xpos=flat(res["xpos"]), xquat=flat(res["xquat"]), marker_sites=flat(res["sites"]),
+            offsets=np.array(self._offsets), names_qpos=self._part_names, names_xpos=self._body_names,
+            kp_data=clips.reshape(C * F, -1), kp_names=self._kp_names,
+        )  # fmt: skip
+
+    # ------------------------------------------------------------------
     def ik_only(self, kp_data, offsets) -> io.StacData:
         """Inverse kinematics with fixed offsets over independent clips (reference ``stac.py:356-454``).
 

@@ -112,3 +112,22 @@ def test_models_without_parts_or_root(engine_of):
         ref = c.oracle(np.float32, 1).pose_clips(kp.reshape(2, F, -1), c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub,
                                                  c.setup.indiv_parts, nthreads=4, **c.root_kw())  # fmt: skip
         np.testing.assert_allclose(d.qpos, ref["qpos"].reshape(2 * F, -1), atol=1e-3, rtol=0)
+
+
+def test_fit_offsets_clip_split_reduces_to_reference_schedule_for_one_clip(rodent):
+    """The opt-in clip-split fit with a single clip IS the reference schedule: same offsets, same poses."""
+    F = 6
+    st = make_stac(rodent, F, n_iters=2)
+    kp, _, _ = rodent.session(F, F, seed=12)
+    a = st.fit_offsets(kp)
+    b = st.fit_offsets_clip_split(kp, n_frames_per_clip=F)
+    np.testing.assert_array_equal(a.offsets, b.offsets)
+    np.testing.assert_array_equal(a.qpos, b.qpos)
+    np.testing.assert_array_equal(a.marker_sites, b.marker_sites)
+    # several clips: independent chains, still a valid fit (offsets move towards the perturbed ground truth)
+    kp2, _, off_true = rodent.session(4 * F, F, seed=13)
+    c = st.fit_offsets_clip_split(kp2, n_frames_per_clip=F)
+    assert c.qpos.shape == (4 * F, rodent.tree.nq) and np.isfinite(c.offsets).all()
+    init = rodent.setup.initial_offsets
+    free = rodent.setup.is_regularized[:, 0] == 0
+    assert np.linalg.norm((c.offsets - off_true)[free]) < np.linalg.norm((init - off_true)[free])
