@@ -131,3 +131,37 @@ def test_fit_offsets_clip_split_reduces_to_reference_schedule_for_one_clip(roden
     init = rodent.setup.initial_offsets
     free = rodent.setup.is_regularized[:, 0] == 0
     assert np.linalg.norm((c.offsets - off_true)[free]) < np.linalg.norm((init - off_true)[free])
+
+
+def test_run_stac_pipeline_end_to_end(rodent, monkeypatch, tmp_path):
+    """load_configs-style cfg -> run_stac: fit_offsets, save, reload, ik_only on overlapping clips, edge cross-fade, qvel.
+    h5py is not installed in this image, so the two io functions are replaced by an in-memory store; everything else is
+    the real pipeline on the GPU."""
+    from stac_mjx_b200 import io, main
+    from stac_mjx_b200.config import Cfg
+
+    F, C = 10, 3
+    cfg = Cfg(rodent.cfg.to_dict())
+    cfg.stac.update(n_frames_per_clip=F, continuous=True, n_fit_frames=6, skip_fit_offsets=False, skip_ik_only=False, infer_qvels=True,
+                    fit_offsets_path="fit.h5", ik_only_path="ik.h5")  # fmt: skip
+    cfg.model.N_ITERS = 1
+    store = {}
+
+    def save(config, file_path, **data):
+        store[str(file_path)] = (config, io.StacData(**{k: data[k] for k in io.StacData.__dataclass_fields__}))
+
+    monkeypatch.setattr(io, "save_data_to_h5", save)
+    monkeypatch.setattr(io, "load_stac_data", lambda p: store[str(p)])
+    kp, _, _ = rodent.session(C * F, F, seed=8)
+    fit_path, ik_path = main.run_stac(cfg, kp, rodent.kp_names, base_path=tmp_path, tree=rodent.tree)
+    fit, ik = store[str(fit_path)][1], store[str(ik_path)][1]
+    assert fit.qpos.shape == (6, rodent.tree.nq) and fit.offsets.shape == (rodent.K, 3)
+    # continuous=True: clips of F+10 frames are solved, the overlaps cross-faded and removed -> exactly C*F frames remain
+    assert ik.qpos.shape == (C * F, rodent.tree.nq) and ik.xpos.shape == (C * F, rodent.tree.nbody, 3)
+    assert ik.marker_sites.shape == (C * F, rodent.K, 3) and ik.qvel.shape == (C * F, rodent.tree.nq - 1)
+    assert np.isfinite(ik.qpos).all() and np.isfinite(ik.qvel).all()
+    np.testing.assert_array_equal(ik.offsets, fit.offsets)
+    # the first clip's first frames are untouched by the cross-fade: they equal a plain IK of that clip with the fitted offsets
+    st = make_stac(rodent, F + 10)
+    ref = st.ik_only(np.concatenate([kp[: F + 10]]), fit.offsets)
+    np.testing.assert_array_equal(ik.qpos[:F], ref.qpos[:F])
