@@ -220,3 +220,24 @@ def test_real_mocap_fixture_is_what_load_data_produces(tmp_path):
     out, names = io.load_data(cfg, base_path=tmp_path)
     assert names == names_model and out.shape == (20, 69) and out.dtype == np.float32
     np.testing.assert_allclose(out, g["kp"][:20], rtol=1e-6, atol=1e-9)
+
+
+def test_package_data_unbatched():
+    # reference tests/unit/test_stac_package.py:11-38
+    from stac_mjx_b200.stac import Stac
+
+    dummy = types.SimpleNamespace(_offsets=np.zeros((2, 3)), _part_names=["root"], _body_names=["body"], _kp_names=["kp1", "kp2"],
+                                  _body_site_idxs=np.array([0, 1]))  # fmt: skip
+    out = Stac._package_data(dummy, None, np.zeros((2, 1)), np.zeros((2, 1, 3)), np.zeros((2, 1, 4)), np.zeros((2, 2, 3)),
+                             np.zeros((2, 6)), batched=False)  # fmt: skip
+    assert out.offsets.shape == (2, 3) and out.kp_names == ["kp1", "kp2"] and out.qpos.shape == (2, 1)
+
+
+def test_velocity_no_freejoint_reference_case():
+    # reference tests/unit/test_utils_math.py: three frames of a linear ramp, dt = 1
+    q = np.array([[0.0, 0.0, 0.0], [1.0, 2.0, 3.0], [2.0, 4.0, 6.0]])
+    v = utils.compute_velocity_from_kinematics(q, dt=1.0, freejoint=False, max_qvel=100.0)
+    assert v.shape == (3, 3)
+    np.testing.assert_allclose(v[0], [1, 2, 3])
+    np.testing.assert_allclose(v[1], [1, 2, 3])
+    np.testing.assert_allclose(v[2], [0, 0, 0])
