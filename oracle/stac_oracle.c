@@ -147,12 +147,14 @@ static inline q4 c_qmul(q4 u, q4 v) {
   r.z = r_fma(u.z, v.w, r_fma(-u.y, v.x, r_fma(u.x, v.y, u.w * v.z)));
   return r;
 }
+/* canonical: one division, x * (1/d); *n_out receives the RECIPROCAL 1/d (the canonical gradient multiplies by it) */
 static inline q4 c_normalize4(q4 q, REAL *n_out) {
   REAL n2 = r_fma(q.z, q.z, r_fma(q.y, q.y, r_fma(q.x, q.x, q.w * q.w)));
   REAL n = r_sqrt(n2);
   REAL d = n + (n == R(0) ? R(1e-6) : R(0));
-  q4 r = { q.w / d, q.x / d, q.y / d, q.z / d };
-  if (n_out) *n_out = d;
+  REAL ri = R(1) / d;
+  q4 r = { q.w * ri, q.x * ri, q.y * ri, q.z * ri };
+  if (n_out) *n_out = ri;
   return r;
 }
 static inline void c_sincos(REAL x, REAL *sp, REAL *cp) {
@@ -270,7 +272,7 @@ typedef struct {
   REAL *res;           /* masked residuals [K*3] */
   REAL *W;             /* wrench scratch [ (K+1) * 6 ] */
   REAL *qfull;         /* [nq] */
-  REAL *fnorm;         /* per-joint norm of raw quaternion (free/ball) [njnt] */
+  REAL *fnorm;         /* per-joint quaternion normalisation: divisor (mode 0) or its reciprocal (mode 1) [njnt] */
 } owork;
 
 static owork *work_create(const omodel *m) {
@@ -528,8 +530,8 @@ static REAL loss_eval(const omodel *m, const osched *s, int mode, owork *w, cons
           q4 qh = ld4(w->Q + 4 * b); q4 tq = { 0, Tp.x, Tp.y, Tp.z };
           q4 h = c_qmul(tq, qh); h.w *= R(2); h.x *= R(2); h.y *= R(2); h.z *= R(2);
           REAL pr = r_fma(qh.z, h.z, r_fma(qh.y, h.y, r_fma(qh.x, h.x, qh.w * h.w))), n = w->fnorm[j];
-          grad[adr + 3] = r_fma(-qh.w, pr, h.w) / n; grad[adr + 4] = r_fma(-qh.x, pr, h.x) / n;
-          grad[adr + 5] = r_fma(-qh.y, pr, h.y) / n; grad[adr + 6] = r_fma(-qh.z, pr, h.z) / n;
+          grad[adr + 3] = r_fma(-qh.w, pr, h.w) * n; grad[adr + 4] = r_fma(-qh.x, pr, h.x) * n;
+          grad[adr + 5] = r_fma(-qh.y, pr, h.y) * n; grad[adr + 6] = r_fma(-qh.z, pr, h.z) * n;
           continue;
         }
         /* world anchor / axis from the parent's world pose */
@@ -545,8 +547,8 @@ static REAL loss_eval(const omodel *m, const osched *s, int mode, owork *w, cons
         q4 ql = ld4(w->qn + adr); q4 tq = { 0, tl.x, tl.y, tl.z };
         q4 h = c_qmul(ql, tq); h.w *= R(2); h.x *= R(2); h.y *= R(2); h.z *= R(2);
         REAL pr = r_fma(ql.z, h.z, r_fma(ql.y, h.y, r_fma(ql.x, h.x, ql.w * h.w))), n = w->fnorm[j];
-        grad[adr] = r_fma(-ql.w, pr, h.w) / n; grad[adr + 1] = r_fma(-ql.x, pr, h.x) / n;
-        grad[adr + 2] = r_fma(-ql.y, pr, h.y) / n; grad[adr + 3] = r_fma(-ql.z, pr, h.z) / n;
+        grad[adr] = r_fma(-ql.w, pr, h.w) * n; grad[adr + 1] = r_fma(-ql.x, pr, h.x) * n;
+        grad[adr + 2] = r_fma(-ql.y, pr, h.y) * n; grad[adr + 3] = r_fma(-ql.z, pr, h.z) * n;
       }
     }
   }

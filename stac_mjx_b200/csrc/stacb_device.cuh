@@ -151,7 +151,7 @@ template <int NB>
 struct Keep {
   V3 anchor[NB][JMAX];  // joint anchor in the parent frame of its body
   V3 axis[NB][JMAX];    // joint axis in the parent frame of its body
-  float fnorm[NB];      // divisor of the quaternion normalisation (free / ball joint)
+  float fnorm[NB];      // reciprocal of the divisor of the quaternion normalisation (free / ball joint)
 };
 
 template <int NB>
@@ -159,7 +159,7 @@ struct FkState {
   V3 P[NB];
   Q4 Q[NB];
   Keep<NB> keep;
-  float fd;  // divisor of the primary free joint's quaternion normalisation (uniform across the warp)
+  float fd;  // reciprocal divisor of the primary free joint's quaternion normalisation (uniform across the warp)
 };
 
 // MJX smooth.kinematics per-body step, evaluated in the parent's frame (canonical order).
@@ -512,13 +512,14 @@ __device__ __forceinline__ void wrench_range(const Chain &ch, int sa, int se, V3
   Tq = mk3(wr[3], wr[4], wr[5]);
 }
 
-// d loss / d (raw quaternion) of a normalised quaternion acted on by world torque `tau` (left-multiplied rotation)
+// d loss / d (raw quaternion) of a normalised quaternion acted on by world torque `tau` (left-multiplied rotation);
+// n is the RECIPROCAL of the normalisation divisor (normalize4)
 __device__ __forceinline__ void quat_grad_left(Q4 qh, V3 tau, float n, float *g4) {
   Q4 h = qmul(mk4(0.f, tau.x, tau.y, tau.z), qh);
   h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
   const float pr = fmaf(qh.z, h.z, fmaf(qh.y, h.y, fmaf(qh.x, h.x, qh.w * h.w)));
-  g4[0] = fmaf(-qh.w, pr, h.w) / n; g4[1] = fmaf(-qh.x, pr, h.x) / n;
-  g4[2] = fmaf(-qh.y, pr, h.y) / n; g4[3] = fmaf(-qh.z, pr, h.z) / n;
+  g4[0] = fmaf(-qh.w, pr, h.w) * n; g4[1] = fmaf(-qh.x, pr, h.x) * n;
+  g4[2] = fmaf(-qh.y, pr, h.y) * n; g4[3] = fmaf(-qh.z, pr, h.z) * n;
 }
 
 // Reverse sweep: each body lane turns the subtree wrench of its joints into d loss / d qpos (into gbuf).
@@ -569,8 +570,8 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
             Q4 h = qmul(ql, mk4(0.f, tl.x, tl.y, tl.z));
             h.w *= 2.0f; h.x *= 2.0f; h.y *= 2.0f; h.z *= 2.0f;
             const float pr = fmaf(ql.z, h.z, fmaf(ql.y, h.y, fmaf(ql.x, h.x, ql.w * h.w))), n = S.keep.fnorm[i];
-            ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) / n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) / n;
-            ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) / n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) / n;
+            ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) * n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) * n;
+            ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) * n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) * n;
           } else {  // an additional free joint
             const V3 Tp = sub3(Tq, cross3(sub3(S.P[i], cref), F));
             float g4[4];

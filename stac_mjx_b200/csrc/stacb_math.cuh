@@ -47,13 +47,15 @@ __device__ __forceinline__ Q4 qmul(Q4 u, Q4 v) {
   return r;
 }
 
-// math.normalize: x / (n + 1e-6 * (n == 0)); returns the divisor through *d_out
-__device__ __forceinline__ Q4 normalize4(Q4 q, float *d_out) {
+// math.normalize: x / (n + 1e-6 * (n == 0)), canonically evaluated as x * (1 / d) with ONE IEEE division;
+// the reciprocal is returned through *rinv_out (the reverse sweep multiplies by it as well).
+__device__ __forceinline__ Q4 normalize4(Q4 q, float *rinv_out) {
   float n2 = fmaf(q.z, q.z, fmaf(q.y, q.y, fmaf(q.x, q.x, q.w * q.w)));
   float n = sqrtf(n2);
   float d = n + (n == 0.0f ? 1e-6f : 0.0f);
-  *d_out = d;
-  return mk4(q.w / d, q.x / d, q.y / d, q.z / d);
+  float r = 1.0f / d;
+  *rinv_out = r;
+  return mk4(q.w * r, q.x * r, q.y * r, q.z * r);
 }
 
 // sin/cos by 3-term Cody-Waite reduction (pi/2) and degree-7/8 minimax polynomials;

@@ -162,6 +162,9 @@ class Stac:
             print(f"Final residual error of {float(res.error)}")
             mjx_model = mjx_model.replace(site_pos=res.params)
             self._offsets = res.params.cpu().numpy()
+            # offset_optimization ends with utils.kinematics (compute_stac.py:163), which normalises the free / ball
+            # quaternions of the carried qpos once more; keep that so a single clip reproduces fit_offsets bit for bit
+            qio = eng.fk(qio, mjx_model.site_pos)[0].contiguous()
         self.last_stats = {"iters": out["iters"], "ls_evals": out["ls_evals"], "status": out["status"]}
         res = {k: out[k] for k in ("qpos", "xpos", "xquat", "sites")}
         if ws > 1:
