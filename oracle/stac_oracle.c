@@ -534,13 +534,18 @@ static REAL loss_eval(const omodel *m, const osched *s, int mode, owork *w, cons
           grad[adr + 5] = r_fma(-qh.y, pr, h.y) * n; grad[adr + 6] = r_fma(-qh.z, pr, h.z) * n;
           continue;
         }
-        /* world anchor / axis from the parent's world pose */
-        v3 A, Wx;
-        if (p != 0) { q4 pq = ld4(w->Q + 4 * p); A = add3(ld3(w->P + 3 * p), c_rotate(ld3(w->anchor + 3 * j), pq)); Wx = c_rotate(ld3(w->axis + 3 * j), pq); }
-        else { A = ld3(w->anchor + 3 * j); Wx = ld3(w->axis + 3 * j); }
-        if (t == JNT_SLIDE) { grad[adr] = c_dot3(Wx, F); continue; }
+        /* hinge / slide: bring the subtree wrench into the PARENT frame once (the parent-frame anchor / axis of
+           every joint of the body are then used directly); world body 0 is the identity pose */
+        q4 pq = ld4(w->Q + 4 * p); v3 pp = ld3(w->P + 3 * p);
+        q4 pc = { pq.w, -pq.x, -pq.y, -pq.z };
+        v3 T0 = sub3(T, c_cross(sub3(pp, cref), F));
+        v3 Fp = c_rotate(F, pc), Tp = c_rotate(T0, pc);
+        v3 al = ld3(w->anchor + 3 * j), xl = ld3(w->axis + 3 * j);
+        if (t == JNT_SLIDE) { grad[adr] = c_dot3(xl, Fp); continue; }
+        if (t == JNT_HINGE) { grad[adr] = c_dot3(xl, sub3(Tp, c_cross(al, Fp))); continue; }
+        /* ball: world-frame anchor, torque about it */
+        v3 A = add3(pp, c_rotate(al, pq));
         v3 d = sub3(A, cref); v3 cr = c_cross(d, F); v3 Ta = sub3(T, cr);
-        if (t == JNT_HINGE) { grad[adr] = c_dot3(Wx, Ta); continue; }
         /* ball */
         q4 qb = ld4(w->Q + 4 * b); q4 qc = { qb.w, -qb.x, -qb.y, -qb.z };
         v3 tl = c_rotate(Ta, qc);

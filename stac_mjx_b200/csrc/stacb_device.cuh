@@ -548,22 +548,28 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
     Q4 pq;
     gather_pose<NB>(ch, S, b.parent >= 0 ? b.parent : 0, pp, pq);
     const bool has_par = b.parent >= 0;
+    pp = sel3(has_par, pp, mk3(0.f, 0.f, 0.f));            // top-level body: the world frame
+    pq = sel4(has_par, pq, mk4(1.f, 0.f, 0.f, 0.f));
+    // every joint of a body shares the body's subtree: one wrench, brought into the parent frame once
+    const int sa = b.jsa[0], se = b.jse[0];
+    const bool live = b.nj > 0 && se > sa;
+    V3 F, Tq;
+    wrench_range(ch, live ? sa : 0, live ? se : 1, F, Tq);
+    const Q4 pc = mk4(pq.w, -pq.x, -pq.y, -pq.z);
+    const V3 T0 = sub3(Tq, cross3(sub3(pp, cref), F));
+    const V3 Fp = rotate(F, pc), Tp = rotate(T0, pc);
 #pragma unroll
     for (int jj = 0; jj < JM; jj++) {
-      const int sa = b.jsa[jj], se = b.jse[jj];
-      const bool live = se > sa;
-      V3 F, Tq;
-      wrench_range(ch, live ? sa : 0, live ? se : 1, F, Tq);
-      const V3 A = sel3(has_par, add3(pp, rotate(S.keep.anchor[i][jj], pq)), S.keep.anchor[i][jj]);
-      const V3 W = sel3(has_par, rotate(S.keep.axis[i][jj], pq), S.keep.axis[i][jj]);
-      const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
-      if (H.hinge[i][jj] && live) ch.gbuf[b.jadr[jj]] = dot3(W, Ta);
+      const V3 al = S.keep.anchor[i][jj], xl = S.keep.axis[i][jj];
+      if (H.hinge[i][jj] && live) ch.gbuf[b.jadr[jj]] = dot3(xl, sub3(Tp, cross3(al, Fp)));
       if (__builtin_expect(ch.T.any_other != 0, 0)) {  // uniform, rare
         if (H.other[i][jj] && live) {
           const int type = b.jtype[jj], adr = b.jadr[jj];
           if (type == STACB_JNT_SLIDE) {
-            ch.gbuf[adr] = dot3(W, F);
+            ch.gbuf[adr] = dot3(xl, Fp);
           } else if (type == STACB_JNT_BALL) {  // right-multiplied local rotation; last joint of its body
+            const V3 A = add3(pp, rotate(al, pq));
+            const V3 Ta = sub3(Tq, cross3(sub3(A, cref), F));
             const Q4 qb = S.Q[i];
             const V3 tl = rotate(Ta, mk4(qb.w, -qb.x, -qb.y, -qb.z));
             const Q4 ql = lds4(ch.qbuf + adr);
@@ -573,9 +579,9 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
             ch.gbuf[adr] = fmaf(-ql.w, pr, h.w) * n; ch.gbuf[adr + 1] = fmaf(-ql.x, pr, h.x) * n;
             ch.gbuf[adr + 2] = fmaf(-ql.y, pr, h.y) * n; ch.gbuf[adr + 3] = fmaf(-ql.z, pr, h.z) * n;
           } else {  // an additional free joint
-            const V3 Tp = sub3(Tq, cross3(sub3(S.P[i], cref), F));
+            const V3 Tf = sub3(Tq, cross3(sub3(S.P[i], cref), F));
             float g4[4];
-            quat_grad_left(S.Q[i], Tp, S.keep.fnorm[i], g4);
+            quat_grad_left(S.Q[i], Tf, S.keep.fnorm[i], g4);
             float *g = ch.gbuf + adr;
             g[0] = F.x; g[1] = F.y; g[2] = F.z; g[3] = g4[0]; g[4] = g4[1]; g[5] = g4[2]; g[6] = g4[3];
           }
