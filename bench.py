@@ -268,7 +268,7 @@ def run_ours(args):
     except Exception:
         pass
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed ncu capture
-    tfile = ROOT / "profiles" / "traffic_r1d_bench_launch.csv"
+    tfile = ROOT / "profiles" / "traffic_r1f_bench_launch.csv"
     if tfile.exists() and args.model == "rodent" and C * F == 18000:
         try:
             import csv
@@ -299,7 +299,7 @@ def run_ours(args):
             },
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic_r1d_bench_launch.csv; outputs mostly still in L2)",
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/traffic_r1f_bench_launch.csv; outputs mostly still in L2)",
                 "note": "FP32 CUDA-core bound path (no tensor-core or HBM-bound kernel exists on it): algorithmic flops (stac_mjx_b200/flops.py, "
                         "SURVEY 8(d)) of one launch / CUDA-event duration; peak = FFMA throughput measured in this run by stacb_fma_peak "
                         "(not in MEASURED_PEAKS.json, which holds HBM and bf16 tensor peaks only)",
