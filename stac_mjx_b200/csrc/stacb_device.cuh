@@ -1,15 +1,15 @@
-// stacb_device.cuh -- fused STAC solver for sm_100a: device code and kernels (ABI in stacb_abi.cu).
+// stacb_device.cuh -- fused STAC solver for sm_100a: device code and kernels (C ABI and dispatch in stacb_abi.cu).
 //
-// One warp owns one chain (a clip, or one independent solve) and runs the whole
-// algorithm in registers + a few KB of shared memory:
-//   FK (parent-frame local transforms, pointer-jumping composition)  -> marker sites ->
-//   masked squared residual -> analytic gradient (prefix-scan subtree wrench, Jacobian
-//   transpose per joint) -> FISTA projected-gradient step with backtracking (jaxopt 0.8.5
-//   ProjectedGradient semantics), frames of a clip strictly sequential with warm start.
-// Replaces reference stac_mjx/stac_core.py:27-99 (q_loss/_q_opt), compute_stac.py:17-104,
-// 170-278 (root/pose optimisation loops), stac_core.py:146-159 (m-phase statistics) and the
-// MJX / jaxopt code underneath them.  Compiled with -fmad=false: every fused multiply-add
-// is explicit, so the arithmetic is the canonical order of DESIGN.md section 4.
+// One chain = one clip (frames strictly sequential, warm-started) or one independent solve.  A warp evaluates
+//   FK (parent-frame local transforms, pointer-jumping composition) -> marker sites -> masked squared residual
+//   -> analytic gradient (prefix-scan subtree wrench, rotated into each body's parent frame, Jacobian transpose per joint)
+// with lane <-> body / site / coordinate mappings fixed for the whole kernel and the tree records in registers, and drives
+// the FISTA projected-gradient solver with backtracking (jaxopt 0.8.5 ProjectedGradient semantics).
+//   throughput modes: one warp per chain (solve);  latency mode: four cooperating warps per chain (solve4).
+// Replaces reference stac_mjx/stac_core.py:27-99 (q_loss/_q_opt), compute_stac.py:17-104,170-278 (root/pose optimisation
+// loops), stac_core.py:146-159 (m-phase statistics) and the MJX / jaxopt code underneath them.  Compiled with -fmad=false:
+// every fused multiply-add is explicit, so the arithmetic is the canonical order of DESIGN.md section 4 and is reproduced
+// bit for bit by the CPU oracle (which is never linked or included here).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>

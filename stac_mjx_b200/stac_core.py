@@ -14,7 +14,6 @@ from dataclasses import dataclass, replace as _dc_replace
 from types import SimpleNamespace
 from typing import Any, NamedTuple
 
-import numpy as np
 import torch
 
 from .engine import Engine

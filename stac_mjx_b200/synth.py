@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .mjcf import JNT_BALL, JNT_FREE, JNT_HINGE, JNT_SLIDE
+from .mjcf import JNT_BALL, JNT_FREE, JNT_HINGE
 from .tree import TreeModel
 
 
