@@ -25,7 +25,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "IK frames/sec (rodent rat23, q-phase over 250-frame clips)"
+METRIC = "IK frames/sec (rodent rat23, whole box) at 1/2/4/8 B200; marker RMSE parity"  # BASELINE.json:metric
 UNIT = "frames/s"
 
 
@@ -79,9 +79,10 @@ def cpu_arm(args, tree, cfg, setup, kp, seconds):
     frames = int(max(4, min(F, seconds / max(per_frame, 1e-6))))
     sample = np.ascontiguousarray(kp[: n_clips * F].reshape(n_clips, F, -1)[:, :frames])
     t0 = time.perf_counter()
-    o.pose_clips(sample, tree.qpos0, setup.initial_offsets, setup.lb, setup.ub, setup.indiv_parts, nthreads=n_clips, **kw)
+    ref = o.pose_clips(sample, tree.qpos0, setup.initial_offsets, setup.lb, setup.ub, setup.indiv_parts, nthreads=n_clips, **kw)
     dt = time.perf_counter() - t0
     return {
+        "_sites": ref["sites"], "_frames": frames, "_clips": n_clips,
         "value": n_clips * frames / dt,
         "unit": UNIT,
         "cores": n_clips,
@@ -284,6 +285,24 @@ def run_ours(args):
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         cpu = cpu_arm(args, tree, cfg, setup, kp, args.cpu_seconds)
         cpu.pop("seconds", None)
+        # marker RMSE parity (the checker role of the oracle): GPU marker sites of the sampled clips vs (a) the CPU port in
+        # MJX operation order just timed -- two float32 orders, so this is the algorithm's rounding noise floor -- and
+        # (b) the canonical-order oracle on a small subset, which the kernels reproduce bit for bit
+        from oracle.oracle import Oracle
+
+        nc, nf = cpu.pop("_clips"), cpu.pop("_frames")
+        gpu_sites = out["sites"][:nc, :nf].cpu().numpy()
+        rmse_mjx = float(np.sqrt(np.mean(np.sum((gpu_sites - cpu.pop("_sites")) ** 2, axis=-1))))
+        sub = np.ascontiguousarray(kp.reshape(C, F, -1)[:2, :20])
+        can = Oracle(tree, setup.site_bodies, np.float32, 1).pose_clips(sub, tree.qpos0, setup.initial_offsets, setup.lb, setup.ub,
+                                                                        setup.indiv_parts, nthreads=2, **kw)
+        d_can = out["sites"][:2, :20].cpu().numpy() - can["sites"]
+        parity = {"marker_rmse_m_vs_cpu_port_mjx_order": rmse_mjx, "sample": f"{nc} clips x {nf} frames",
+                  "marker_rmse_m_vs_canonical_oracle": float(np.sqrt(np.mean(np.sum(d_can**2, axis=-1)))),
+                  "max_abs_qpos_diff_vs_canonical_oracle": float(np.abs(out["qpos"][:2, :20].cpu().numpy() - can["qpos"]).max()),
+                  "canonical_sample": "2 clips x 20 frames", "tolerance_m": 1e-4}
+    else:
+        parity = None
 
     if rank == 0:
         line = {
@@ -307,7 +326,7 @@ def run_ours(args):
                 "hbm": {"achieved_GBs": hbm_step / kernel_s / 1e9, "peak_GBs": peaks.get("hbm_gbs"), "algorithmic_bytes_per_launch": hbm_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
             },
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps,  # one fused stacb::pose_clips_kernel launch per step
             "clocks": sampler.summary(),
