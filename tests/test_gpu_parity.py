@@ -339,3 +339,36 @@ def test_all_joint_types_on_gpu():
     finally:
         eng.set_mode(-1)
     np.testing.assert_allclose(np.linalg.norm(ref["qpos"][..., 3:7], axis=-1), 1.0, atol=1e-6)
+
+
+def test_slide_root_model_uses_four_root_dofs():
+    """A model whose first joint is a slide (the reference's root_dims = 4 branch, compute_stac.py:51-54)."""
+    from oracle.oracle import Oracle
+    from stac_mjx_b200 import mjcf, tree
+    from stac_mjx_b200.engine import Engine
+
+    xml = """<mujoco><compiler angle="radian"/><worldbody>
+      <body name="cart" pos="0 0 0.1">
+        <joint name="sx" type="slide" axis="1 0 0"/><joint name="sy" type="slide" axis="0 1 0"/><joint name="yaw" type="hinge" axis="0 0 1"/>
+        <site name="k0" pos="0.02 0 0.01"/>
+        <body name="pole" pos="0 0 0.05"><joint name="tilt" type="hinge" axis="0 1 0" range="-1 1"/><site name="k1" pos="0 0.01 0.2"/>
+          <body name="tip" pos="0 0 0.3"><joint name="bend" type="hinge" axis="1 0 0" range="-1 1"/><site name="k2" pos="0.01 0 0.1"/></body>
+        </body>
+      </body></worldbody></mujoco>"""
+    t = tree.compile_spec(mjcf.parse_mjcf(xml, from_string=True))
+    sidx = np.array([t.site_id(n) for n in ("k0", "k1", "k2")])
+    sb, off = t.site_bodyid[sidx], t.site_pos[sidx].astype(np.float32)
+    lb, ub, _ = tree.align_joint_dims(t.jnt_type, t.jnt_range, t.jnt_names)
+    assert int(t.jnt_type[0]) == 2 and t.nq == 5
+    eng, o = Engine(t, sb, 0), Oracle(t, sb, np.float32, 1)
+    rng = np.random.default_rng(4)
+    qt = rng.normal(scale=0.3, size=(2, 4, t.nq)).astype(np.float32)
+    kp = np.stack([[o.fk(qt[c, f], off)[3].reshape(-1) for f in range(4)] for c in range(2)]).astype(np.float32)
+    kw = dict(do_root=1, root_kp_idx=0, trunk_kps=np.array([1, 1, 0], bool), root_dims=4, tol=1e-6, maxiter=100)
+    qio = torch.zeros(2, t.nq, device=eng.device)
+    out = eng.pose_clips(kp, qio, off, lb, ub, np.zeros((0, t.nq), bool), **kw)
+    ref = o.pose_clips(kp, np.zeros(t.nq), off, lb, ub, [], **kw)
+    np.testing.assert_array_equal(npy(out["root_stats"]), ref["root_stats"])
+    for k in ("qpos", "sites", "err", "iters"):
+        np.testing.assert_array_equal(npy(out[k]), ref[k])
+    assert np.abs(npy(out["sites"]) - kp.reshape(2, 4, 3, 3)).max() < 2e-3
