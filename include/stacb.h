@@ -130,7 +130,8 @@ int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream)
 
 /* Scheduling of stacb_pose_clips: -1 auto (default), 0 throughput mode (one warp per clip chain),
  * 1 latency mode (four cooperating warps per chain, speculative line search), 2 dense throughput mode (registers
- * capped so 16 chains fit per SM; chosen automatically from 16 chains per SM). Results are bit-identical. */
+ * capped so 16 chains fit per SM; chosen automatically from 16 chains per SM), 3 grouped latency mode (wide trees: each of
+ * the four speculative evaluations is carried out by three warps sharing the bodies). Results are bit-identical. */
 int stacb_set_mode(int mode);
 
 const char *stacb_last_error(void);

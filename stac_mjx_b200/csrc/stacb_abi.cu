@@ -229,7 +229,7 @@ static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl, int jm)
   return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl && t->jm_act <= jm;
 }
 
-static int g_force_mode = -1;  // -1 auto, 0 throughput, 1 latency (four warps per chain), 2 dense throughput (128 registers)
+static int g_force_mode = -1;  // -1 auto, 0 throughput, 1 latency (four warps per chain), 2 dense throughput, 3 grouped latency
 
 static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
   CUDA_TRY(cudaSetDevice(t->device));
@@ -239,13 +239,17 @@ static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
   // Few chains: latency mode, one CTA of four cooperating warps per chain (speculative line search, see solve4).
   // Many chains: throughput mode, one warp per chain, four chains per CTA.
   const size_t chain_bytes = (size_t)chain_smem_floats(t->T) * 4;
-  const size_t coop_bytes = 4 * chain_bytes + ((size_t)t->T.nqp + 8) * 4;
+  const size_t coop_extra = ((size_t)t->T.nqp + 8) * 4;
+  const size_t coop_bytes = 4 * chain_bytes + coop_extra;
+  const size_t grouped_bytes = (4 * (size_t)role_smem_floats(t->T) + 4 * GRP * (size_t)warp_smem_floats(t->T)) * 4 + coop_extra;
   int coop = (a.C <= 2 * sms) ? 1 : (a.C >= 16 * sms ? 2 : 0);
   if (g_force_mode >= 0) coop = g_force_mode;
+  if (coop == 1 && g_force_mode < 0 && t->bpl_act > 1 && a.C <= sms) coop = 3;  // wide tree, few chains: grouped latency mode
+  if (coop == 3 && (t->bpl_act <= 1 || grouped_bytes > 200 * 1024)) coop = 1;
   if (coop == 1 && coop_bytes > 200 * 1024) coop = 0;
-  const int wpb = 4;
-  const int grid = coop == 1 ? std::min(a.C, sms * 8) : std::min((a.C + wpb - 1) / wpb, sms * 16);
-  const size_t smem = coop == 1 ? coop_bytes : wpb * chain_bytes;
+  const int wpb = coop == 3 ? 4 * GRP : 4;
+  const int grid = (coop == 1 || coop == 3) ? std::min(a.C, sms * 8) : std::min((a.C + wpb - 1) / wpb, sms * 16);
+  const size_t smem = coop == 3 ? grouped_bytes : (coop == 1 ? coop_bytes : wpb * chain_bytes);
   if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
 #define X(c, n, f, p, j) \
   if (fits(t, c, n, f, p, j)) { CUDA_TRY(launch_pose_##c##_##n##_##f##_##p##_##j(t->T, a, grid, 32 * wpb, smem, coop, s)); return STACB_OK; }
@@ -335,7 +339,7 @@ extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, vo
 }
 
 extern "C" int stacb_set_mode(int mode) {
-  if (mode < -1 || mode > 2) return fail(STACB_E_INVALID, "stacb_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency) or 2 (dense throughput)");
+  if (mode < -1 || mode > 3) return fail(STACB_E_INVALID, "stacb_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency), 2 (dense throughput) or 3 (grouped latency)");
   g_force_mode = mode;
   return STACB_OK;
 }

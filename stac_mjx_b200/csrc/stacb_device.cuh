@@ -47,18 +47,32 @@ struct DevTree {
   const int *quat_adr;    // [nquat] qpos address of each quaternion
 };
 
-__host__ __device__ inline int chain_smem_floats(const DevTree &T) { return 2 * T.nqp + 7 * T.pqn + 6 * T.npre; }
+__host__ __device__ inline int role_smem_floats(const DevTree &T) { return 2 * T.nqp + 7 * T.pqn; }  // qbuf, gbuf, PQ
+__host__ __device__ inline int warp_smem_floats(const DevTree &T) { return 6 * T.npre; }               // Ipre
+__host__ __device__ inline int chain_smem_floats(const DevTree &T) { return role_smem_floats(T) + warp_smem_floats(T); }
 
+// Per-evaluation scratch in shared memory. One "role" = one evaluation of the loss; it is carried out by G member warps
+// (G = 1 everywhere except the grouped latency mode for wide trees, where the bodies of the tree are dealt out over
+// G = 3 warps).  qbuf / gbuf / PQ are shared by the members of a role, Ipre is private to each warp.
 struct Chain {
   const DevTree &T;
   int lane;
+  int g, G, bar;  // member index, members per role, named barrier of the role
   float *qbuf, *gbuf, *PQ, *Ipre;
-  __device__ Chain(const DevTree &t, float *base, int ln) : T(t), lane(ln) {
-    qbuf = base;
+  __device__ Chain(const DevTree &t, float *role_base, float *warp_base, int ln, int g_, int G_, int bar_)
+      : T(t), lane(ln), g(g_), G(G_), bar(bar_) {
+    qbuf = role_base;
     gbuf = qbuf + t.nqp;
     PQ = gbuf + t.nqp;
-    Ipre = PQ + 7 * t.pqn;
+    Ipre = warp_base;
   }
+  // barrier among the members of the role (a warp-level fence when the role is a single warp)
+  __device__ __forceinline__ void sync() const {
+    if (G == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * G) : "memory");
+  }
+  // active-set element handled by this lane in slot i
+  __device__ __forceinline__ int elem(int i) const { return lane + 32 * (g + G * i); }
 };
 
 __device__ __forceinline__ float ldf(const int *p) { return __int_as_float(__ldg(p)); }
@@ -111,11 +125,12 @@ struct Hot {
 };
 
 template <int NB>
-__device__ __forceinline__ void hot_init(Hot<NB> &H, const DevTree &T, int lane) {
+__device__ __forceinline__ void hot_init(Hot<NB> &H, const Chain &ch) {
+  const DevTree &T = ch.T;
   const DevSet &S = T.act;
 #pragma unroll
   for (int i = 0; i < NB; i++) {
-    const int e = lane + 32 * i;
+    const int e = ch.elem(i);
     H.on[i] = e < S.n;
     load_body(H.bc[i], S.rec + (size_t)(H.on[i] ? e : 0) * REC);
     if (!H.on[i]) { H.bc[i].nj = 0; H.bc[i].parent = -1; }
@@ -267,7 +282,7 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
             pos = sub3(anchor, rotate(jpos, quat));
           } else {  // slide
             const V3 axis = rotate(jaxis, quat);
-            const float d = ch.qbuf[adr] - ldf(ch.T.act.rec + (size_t)(ch.lane + 32 * i) * REC + R_JNT + J_STRIDE * jj + J_REF);
+            const float d = ch.qbuf[adr] - ldf(ch.T.act.rec + (size_t)ch.elem(i) * REC + R_JNT + J_STRIDE * jj + J_REF);
             pos = mk3(fmaf(axis.x, d, pos.x), fmaf(axis.y, d, pos.y), fmaf(axis.z, d, pos.z));
           }
         }
@@ -275,7 +290,7 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
     }
     S.P[i] = pos;
     S.Q[i] = quat;
-    if (ch.T.free_e >= 0) __syncwarp();  // every lane has read the raw quaternion before its owner overwrites it
+    if (ch.T.free_e >= 0) ch.sync();  // every lane of the role has read the raw quaternion before its owner overwrites it
     if (H.pfree[i]) {  // MJX writes the normalised quaternion back into qpos
       const int fa = ch.T.free_adr;
       ch.qbuf[fa + 3] = fq.w; ch.qbuf[fa + 4] = fq.x; ch.qbuf[fa + 5] = fq.y; ch.qbuf[fa + 6] = fq.z;
@@ -297,8 +312,8 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
     for (int r = 0; r < rounds; r++) {
 #pragma unroll
       for (int i = 0; i < NB; i++)
-        if (H.on[i]) sts7(ch.PQ + 7 * (ch.lane + 32 * i), S.P[i], S.Q[i]);
-      __syncwarp();
+        if (H.on[i]) sts7(ch.PQ + 7 * ch.elem(i), S.P[i], S.Q[i]);
+      ch.sync();
 #pragma unroll
       for (int i = 0; i < NB; i++) {
         const int a = hot_anc<NB>(H, i, r);
@@ -308,12 +323,12 @@ __device__ __forceinline__ void fk_hot(const Chain &ch, const Hot<NB> &H, FkStat
         S.P[i] = sel3(a >= 0, add3(pa, rotate(S.P[i], qa)), S.P[i]);
         S.Q[i] = sel4(a >= 0, qmul(qa, S.Q[i]), S.Q[i]);
       }
-      __syncwarp();
+      ch.sync();
     }
 #pragma unroll
     for (int i = 0; i < NB; i++)
-      if (H.on[i]) sts7(ch.PQ + 7 * (ch.lane + 32 * i), S.P[i], S.Q[i]);
-    __syncwarp();
+      if (H.on[i]) sts7(ch.PQ + 7 * ch.elem(i), S.P[i], S.Q[i]);
+    ch.sync();
   }
 }
 
@@ -536,7 +551,7 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
     const V3 Tp = sub3(Tq, cross3(sub3(fp, cref), F));
     float g4[4];
     quat_grad_left(fq, Tp, fn, g4);
-    if (ch.lane == 0) {
+    if (ch.lane == 0 && ch.g == 0) {
       float *g = ch.gbuf + ch.T.free_adr;
       g[0] = F.x; g[1] = F.y; g[2] = F.z; g[3] = g4[0]; g[4] = g4[1]; g[5] = g4[2]; g[6] = g4[3];
     }
@@ -589,7 +604,7 @@ __device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, c
       }
     }
   }
-  __syncwarp();
+  ch.sync();
 }
 
 // Solver-side per-lane state: coordinate i = lane + 32*m lives in slot m.
@@ -605,10 +620,12 @@ template <int CPL, int NB, int SPL>
 __device__ __forceinline__ float eval_fwd(const Chain &ch, const Coords<CPL> &co, const Hot<NB> &H, const float (&pt)[CPL],
                                           const float (&q0)[CPL], unsigned maskbits, const Sites<SPL> &st, FkState<NB> &S,
                                           SiteVals<SPL> &sv) {
+  if (ch.g == 0) {
 #pragma unroll
-  for (int m = 0; m < CPL; m++)
-    if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = ((maskbits >> m) & 1u) ? pt[m] : q0[m];
-  __syncwarp();
+    for (int m = 0; m < CPL; m++)
+      if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = ((maskbits >> m) & 1u) ? pt[m] : q0[m];
+  }
+  ch.sync();
   fk_hot<NB, true>(ch, H, S);
   return sites_loss<NB, SPL>(ch, S, st, sv);
 }
@@ -780,7 +797,7 @@ __device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, cons
       const float dec = stp_m * (f - fy);
       const float cond = fmaf(stp_m, dg, 0.5f * sq);
       const bool rejected = (dec > cond + 1.1920929e-07f) && (base + w < maxls);
-      if (ch.lane == 0) {
+      if (ch.lane == 0 && ch.g == 0) {
         cp.sc[w] = rejected ? 0.f : 1.f;
         if (!(f - f == 0.0f)) cp.sc[4] = 1.f;
       }
@@ -805,12 +822,14 @@ __device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, cons
           d[m] = co.valid[m] ? clipf(xk - gt[m], co.lb[m], co.ub[m]) - xk : 0.f;
         }
         const float err = sqrtf(warp_sum(lane_dot<CPL>(d, d)));
-        if (ch.lane == 0) cp.sc[2] = err;
+        if (ch.lane == 0 && ch.g == 0) cp.sc[2] = err;
       } else {  // gradient at y' -> next iteration
+        if (ch.g == 0) {
 #pragma unroll
-        for (int m = 0; m < CPL; m++)
-          if (co.valid[m]) cp.g[ch.lane + 32 * m] = gt[m];
-        if (ch.lane == 0) cp.sc[3] = f;
+          for (int m = 0; m < CPL; m++)
+            if (co.valid[m]) cp.g[ch.lane + 32 * m] = gt[m];
+          if (ch.lane == 0) cp.sc[3] = f;
+        }
       }
     }
     __syncthreads();
@@ -839,21 +858,23 @@ __device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, cons
 template <int CPL>
 __device__ __forceinline__ void normalize_qpos(const Chain &ch, const Coords<CPL> &co, float (&q)[CPL]) {
   if (ch.T.nquat == 0) return;
+  if (ch.g == 0) {
 #pragma unroll
-  for (int m = 0; m < CPL; m++)
-    if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = q[m];
-  __syncwarp();
-  for (int j = ch.lane; j < ch.T.nquat; j += 32) {
-    const int a = __ldg(ch.T.quat_adr + j);
-    float dd;
-    const Q4 qn = normalize4(lds4(ch.qbuf + a), &dd);
-    ch.qbuf[a] = qn.w; ch.qbuf[a + 1] = qn.x; ch.qbuf[a + 2] = qn.y; ch.qbuf[a + 3] = qn.z;
+    for (int m = 0; m < CPL; m++)
+      if (co.valid[m]) ch.qbuf[ch.lane + 32 * m] = q[m];
+    __syncwarp();
+    for (int j = ch.lane; j < ch.T.nquat; j += 32) {
+      const int a = __ldg(ch.T.quat_adr + j);
+      float dd;
+      const Q4 qn = normalize4(lds4(ch.qbuf + a), &dd);
+      ch.qbuf[a] = qn.w; ch.qbuf[a + 1] = qn.x; ch.qbuf[a + 2] = qn.y; ch.qbuf[a + 3] = qn.z;
+    }
   }
-  __syncwarp();
+  ch.sync();
 #pragma unroll
   for (int m = 0; m < CPL; m++)
     if (co.valid[m]) q[m] = ch.qbuf[ch.lane + 32 * m];
-  __syncwarp();
+  ch.sync();
 }
 
 template <int CPL>
@@ -931,25 +952,31 @@ struct PoseArgs {
 };
 
 // MODE 0: throughput (one warp per chain, 4 chains per CTA); MODE 1: latency (4 cooperating warps per chain);
-// MODE 2: dense throughput (registers capped at 128 so 16 warps fit per SM; pays off from ~16 chains per SM).
+// MODE 2: dense throughput (registers capped at 128 so 16 warps fit per SM; pays off from ~16 chains per SM);
+// MODE 3: grouped latency for wide trees: the 4 roles of latency mode, each carried out by GRP = 3 member warps that
+//         deal the bodies of the tree out among themselves (NB is then the number of bodies per lane of ONE member).
+constexpr int GRP = 3;
 template <int CPL, int NB, int NBF, int SPL, int MODE>
-__global__ void __launch_bounds__(128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevTree T, PoseArgs a) {
-  constexpr bool COOP = MODE == 1;
+__global__ void __launch_bounds__(MODE == 3 ? 128 * GRP : 128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevTree T, PoseArgs a) {
+  constexpr bool COOP = MODE == 1 || MODE == 3;
+  constexpr int G = MODE == 3 ? GRP : 1;
   extern __shared__ float smem[];
   __shared__ int s_chain;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  Chain ch(T, smem + (size_t)wib * chain_smem_floats(T), lane);
+  const int role = wib / G, gmem = wib % G;  // 4 roles per CTA: chains (throughput modes) or speculative evaluations (latency modes)
+  float *warp_area = smem + (size_t)4 * role_smem_floats(T);
+  Chain ch(T, smem + (size_t)role * role_smem_floats(T), warp_area + (size_t)wib * warp_smem_floats(T), lane, gmem, G, 1 + role);
   Coop cp;
-  cp.g = smem + (size_t)4 * chain_smem_floats(T);
+  cp.g = warp_area + (size_t)4 * G * warp_smem_floats(T);
   cp.sc = cp.g + T.nqp;
-  cp.w = wib;
-  const bool writer = !COOP || wib == 0;  // latency mode: the four warps hold identical state, warp 0 writes the outputs
+  cp.w = role;
+  const bool writer = !COOP || wib == 0;  // latency modes: every warp holds identical solver state, warp 0 writes the outputs
   Coords<CPL> co;
   coords_init<CPL>(ch, co, a.lb, a.ub);
   Sites<SPL> st;
   sites_init<SPL>(ch, st, a.site_pos);
   Hot<NB> H;
-  hot_init<NB>(H, T, lane);
+  hot_init<NB>(H, ch);
   const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P;
   const unsigned full_bits = mask_bits_u8<CPL>(ch, co, nullptr);
   unsigned root_bits = 0;
@@ -972,9 +999,11 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevT
       c = __shfl_sync(0xffffffffu, c, 0);
     }
     if (c >= a.C) break;
-    for (int m = 0; m < CPL; m++)
-      if (co.valid[m]) ch.gbuf[lane + 32 * m] = 0.f;
-    __syncwarp();
+    if (ch.g == 0) {
+      for (int m = 0; m < CPL; m++)
+        if (co.valid[m]) ch.gbuf[lane + 32 * m] = 0.f;
+    }
+    ch.sync();
     float q[CPL], q0[CPL], x[CPL];
 #pragma unroll
     for (int m = 0; m < CPL; m++) q[m] = co.valid[m] ? a.qpos_io[(size_t)c * nq + lane + 32 * m] : 0.f;
@@ -1011,12 +1040,23 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevT
         const size_t fi = (size_t)c * a.F + f;
         if (a.iters && lane == 0 && writer) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
         // replace_qs: kinematics normalises the quaternions; the last stage's FK also yields the frame outputs
-        if (sg < a.P || !writer) {
+        if (sg < a.P || (role != 0 && COOP)) {
           normalize_qpos<CPL>(ch, co, q);
-        } else {
-          full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
-                                      a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
-          if (a.err && lane == 0) a.err[fi] = so.err;
+        } else {  // the role that writes: its member 0 runs the full-model FK (which also normalises), the others pick q up
+          if (writer) {
+            full_outputs<CPL, NBF, SPL>(ch, co, q, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
+                                        a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
+            if (a.err && lane == 0) a.err[fi] = so.err;
+          }
+          if (G > 1) {
+            ch.sync();
+            if (ch.g != 0) {
+#pragma unroll
+              for (int m = 0; m < CPL; m++)
+                if (co.valid[m]) q[m] = ch.qbuf[lane + 32 * m];
+            }
+            ch.sync();
+          }
         }
       }
     }
@@ -1039,13 +1079,15 @@ template <int CPL, int NB, int NBF, int SPL>
 __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  Chain ch(T, smem + (size_t)wib * chain_smem_floats(T), lane);
+  const int wpb0 = blockDim.x >> 5;
+  Chain ch(T, smem + (size_t)wib * role_smem_floats(T), smem + (size_t)wpb0 * role_smem_floats(T) + (size_t)wib * warp_smem_floats(T), lane, 0, 1,
+           1 + wib);
   Coords<CPL> co;
   coords_init<CPL>(ch, co, a.lb, a.ub);
   Sites<SPL> st;
   sites_init<SPL>(ch, st, a.site_pos);
   Hot<NB> H;
-  hot_init<NB>(H, T, lane);
+  hot_init<NB>(H, ch);
   const int nq = T.nq, K = T.K, nb = T.nbody;
   const int wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + wib; b < a.B; b += gridDim.x * wpb) {

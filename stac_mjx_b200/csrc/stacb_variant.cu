@@ -10,8 +10,13 @@ namespace stacb {
 
 cudaError_t FN(launch_pose_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T, const PoseArgs &a, int grid, int block, size_t smem, int coop,
                                                         cudaStream_t s) {
+  // grouped latency mode (3): each of the GRP member warps of a role carries ceil(V_NB / GRP) bodies per lane (at least 2, so
+  // the shared-memory pose exchange is used); only instantiated for variants with more than one body per lane
+  constexpr int NBG = (V_NB + GRP - 1) / GRP < 2 ? 2 : (V_NB + GRP - 1) / GRP;
   auto k = coop == 1 ? pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 1>
-         : coop == 2 ? pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 2> : pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 0>;
+         : coop == 2 ? pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 2>
+         : (coop == 3 && V_NB > 1) ? pose_clips_kernel<V_CPL, (V_NB > 1 ? NBG : V_NB), V_NBF, V_SPL, (V_NB > 1 ? 3 : 0)>
+                                   : pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 0>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

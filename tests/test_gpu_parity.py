@@ -94,7 +94,8 @@ def test_clips_match_golden(name, engine_of):
 
 @pytest.mark.parametrize("name", ["rodent", "fly_treadmill", "mouse"])
 def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
-    """Throughput (0), latency (1: four cooperating warps, speculative line search) and dense throughput (2) modes:
+    """Throughput (0), latency (1: four cooperating warps, speculative line search), dense throughput (2) and grouped
+    latency (3: three member warps per evaluation for wide trees; falls back to 1 for one-body-per-lane models) modes:
     same bits, same counters."""
     c = get_case(name)
     eng = engine_of(c)
@@ -103,7 +104,7 @@ def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
     kp = kp.reshape(5, F, -1)
     outs = []
     try:
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             eng.set_mode(mode)
             qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (5, 1)), device=eng.device)
             o = eng.pose_clips(kp, qio, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
@@ -111,7 +112,7 @@ def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
     finally:
         eng.set_mode(-1)
     for k in outs[0]:
-        assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[0][k], outs[2][k]), k
+        assert all(np.array_equal(outs[0][k], o[k]) for o in outs[1:]), k
     ref = c.oracle(np.float32, 1).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
                                               nthreads=4, **c.root_kw())  # fmt: skip
     np.testing.assert_allclose(outs[1]["qpos"], ref["qpos"], atol=QPOS_TOL, rtol=0)
