@@ -541,8 +541,8 @@ __device__ __forceinline__ void quat_grad_left(Q4 qh, V3 tau, float n, float *g4
 // Hinges are straight-line code with predicated stores; the primary free joint is evaluated by every lane
 // (uniform) and stored by lane 0; other joint types take a divergent path skipped when the model has none.
 template <int NB>
-__device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, const FkState<NB> &S, V3 cref) {
-  if (ch.T.free_e >= 0 && ch.T.free_se > ch.T.free_sa) {  // uniform
+__device__ __forceinline__ void joint_grads(const Chain &ch, const Hot<NB> &H, const FkState<NB> &S, V3 cref, bool free_wanted) {
+  if (free_wanted && ch.T.free_e >= 0 && ch.T.free_se > ch.T.free_sa) {  // uniform
     V3 F, Tq, fp;
     Q4 fq;
     wrench_range(ch, ch.T.free_sa, ch.T.free_se, F, Tq);
@@ -638,7 +638,16 @@ __device__ __forceinline__ void eval_bwd(const Chain &ch, const Coords<CPL> &co,
   Q4 cq;
   gather_pose<NB>(ch, S, 0, cref, cq);
   wrench_prefix<SPL>(ch, st, sv, cref);
-  joint_grads<NB>(ch, H, S, cref);
+  // the free-joint gradient is skipped when none of its coordinates is optimised (every part solve): the masked entries
+  // of the gradient are zero by definition (stac_core.py:52, make_qs), so nothing observable changes
+  bool mine = false;
+#pragma unroll
+  for (int m = 0; m < CPL; m++) {
+    const int i = ch.lane + 32 * m;
+    mine |= ((maskbits >> m) & 1u) && i >= ch.T.free_adr && i < ch.T.free_adr + 7;
+  }
+  const bool free_wanted = __any_sync(0xffffffffu, mine);
+  joint_grads<NB>(ch, H, S, cref, free_wanted);
 #pragma unroll
   for (int m = 0; m < CPL; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? ch.gbuf[ch.lane + 32 * m] : 0.f;
 }
