@@ -373,3 +373,19 @@ def test_slide_root_model_uses_four_root_dofs():
     for k in ("qpos", "sites", "err", "iters"):
         np.testing.assert_array_equal(npy(out[k]), ref[k])
     assert np.isfinite(npy(out["qpos"])).all()
+
+
+def test_c_abi_without_torch(rodent):
+    """The C ABI driven with cuda-python device memory and ctypes only (no torch types cross the boundary)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("abi_demo_no_torch", ROOT / "tools" / "abi_demo_no_torch.py")
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    r = demo.run(n_clips=2, n_frames=3, seed=3)
+    s = rodent.setup
+    ref = rodent.oracle(np.float32, 1).pose_clips(r["kp"], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=2,
+                                                  **rodent.root_kw())  # fmt: skip
+    np.testing.assert_array_equal(r["iters"], ref["iters"])
+    np.testing.assert_allclose(r["qpos"], ref["qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(r["sites"], ref["sites"], atol=MARKER_TOL, rtol=0)
