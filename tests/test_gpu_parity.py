@@ -389,3 +389,19 @@ def test_c_abi_without_torch(rodent):
     np.testing.assert_array_equal(r["iters"], ref["iters"])
     np.testing.assert_allclose(r["qpos"], ref["qpos"], atol=QPOS_TOL, rtol=0)
     np.testing.assert_allclose(r["sites"], ref["sites"], atol=MARKER_TOL, rtol=0)
+
+
+def test_fly_tethered_config_against_live_oracle(engine_of):
+    """BASELINE config 4's second fruitfly configuration (30 keypoints, no root optimisation key): 2 clips x 5 frames."""
+    c = get_case("fly_tethered")
+    eng = engine_of(c)
+    kp, _, _ = c.session(10, 5, seed=21)
+    kp = kp.reshape(2, 5, -1)
+    qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (2, 1)), device=eng.device)
+    out = eng.pose_clips(kp, qio, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
+    ref = c.oracle(np.float32, 1).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
+                                              nthreads=2, **c.root_kw())  # fmt: skip
+    np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
+    np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(npy(out["sites"]), ref["sites"], atol=MARKER_TOL, rtol=0)
+    assert np.array_equal(npy(out["qpos"]), ref["qpos"])
