@@ -777,11 +777,13 @@ __device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, cons
   eval_bwd<CPL, NB, SPL>(ch, co, H, maskbits, st, S, sv, g);
   int base = 0;
   float stp_a = step;
+  // FISTA momentum of the current iteration; for the following iterations the two roles that idle during the reverse
+  // phase compute it (same operations) and hand it over through cp.sc[5..6]
+  float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+  float beta = (t - 1.0f) / tn;
   for (;;) {
     const float stp_b = stp_a * 0.5f;
     const float stp_m = (w & 1) ? stp_b : stp_a;
-    const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
-    const float beta = (t - 1.0f) / tn;
     float sq = 0.f, dg = 0.f;
 #pragma unroll
     for (int m = 0; m < CPL; m++) {
@@ -840,6 +842,10 @@ __device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, cons
           if (ch.lane == 0) cp.sc[3] = f;
         }
       }
+    } else if (w == 1 - k) {  // an idle role: next iteration's momentum, t_next = tn
+      const float tn2 = 0.5f * (1.0f + sqrtf(fmaf(4.0f * tn, tn, 1.0f)));
+      const float beta2 = (tn - 1.0f) / tn2;
+      if (ch.lane == 0 && ch.g == 0) { cp.sc[5] = tn2; cp.sc[6] = beta2; }
     }
     __syncthreads();
 #pragma unroll
@@ -852,6 +858,8 @@ __device__ __forceinline__ SolveOut solve4(const Chain &ch, const Coop &cp, cons
     fy = cp.sc[3];
     out.err = cp.sc[2];
     t = tn;
+    tn = cp.sc[5];
+    beta = cp.sc[6];
     step = (stp_k <= 1e-6f) ? 1.0f : stp_k / 0.5f;
     out.iters++;
     if (!(out.err > tol && out.iters < maxiter)) break;
