@@ -22,3 +22,12 @@ cat _obj/*.log
 [ $rc -eq 0 ] || { echo "stacb build failed"; exit 1; }
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libstacb.so _obj/*.o
 echo "built $(cd .. && pwd)/libstacb.so"
+# optional: XLA FFI handlers for a JAX host, only where jaxlib's FFI headers exist (not in the authoring image)
+XLA_INC=$(python -c "import jax.ffi; print(jax.ffi.include_dir())" 2>/dev/null || true)
+if [ -n "$XLA_INC" ] && [ -d "$XLA_INC" ]; then
+  g++ -O2 -std=c++17 -fPIC -shared -I "$XLA_INC" -I ../../include -I /usr/local/cuda/include stacb_xla_ffi.cc \
+      -L.. -l:libstacb.so -Wl,-rpath,'$ORIGIN' -L/usr/local/cuda/lib64 -lcudart -o ../libstacb_xla_ffi.so \
+    && echo "built $(cd .. && pwd)/libstacb_xla_ffi.so"
+else
+  echo "jaxlib FFI headers not found: skipping libstacb_xla_ffi.so (stacb_xla_ffi.cc is not compiled in this image)"
+fi

@@ -63,3 +63,18 @@ def test_engine_fails_loudly_without_cuda():
     c = get_case("synth_data")
     with pytest.raises(_lib.StacbError):
         Engine(c.tree, c.setup.site_bodies)
+
+
+def test_jax_ffi_front_end_is_guarded():
+    """No jax in this image: the FFI front-end reports unavailable and refuses loudly instead of falling back."""
+    from stac_mjx_b200 import jax_ffi
+
+    try:
+        import jax.ffi  # noqa: F401
+
+        pytest.skip("jax is installed here")
+    except ImportError:
+        pass
+    assert jax_ffi.available() is False
+    with pytest.raises(RuntimeError, match="JAX FFI path unavailable"):
+        jax_ffi.register()
