@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
 
 #include "stacb.h"
 #include "stacb_device.cuh"
@@ -59,8 +60,11 @@ struct stacb_tree {
   DevTree T;
   int cpl, bpl_act, bpl_full, jm_act;
   std::vector<void *> allocs;
-  int *counter;
+  int *counter;                          // pool of work counters: one per in-flight launch (launches may overlap on different streams)
+  mutable std::atomic<unsigned> next{0};
 };
+
+constexpr int kCounterPool = 64;
 
 static int ceil_log2(int x) { int r = 0; while ((1 << r) < x) r++; return r; }
 
@@ -202,7 +206,7 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   t->cpl = (m.nq + 31) / 32; t->bpl_act = (T.act.n + 31) / 32; t->bpl_full = (T.full.n + 31) / 32;
   T.nqp = 32 * t->cpl; T.pqn = std::max(T.act.n, T.full.n); T.npre = 32 * T.spl;
   void *cnt = nullptr;
-  if (cudaMalloc(&cnt, sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
+  if (cudaMalloc(&cnt, kCounterPool * sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
   t->allocs.push_back(cnt);
   t->counter = (int *)cnt;
   *out = t;
@@ -231,9 +235,10 @@ static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl, int jm)
 
 static int g_force_mode = -1;  // -1 auto, 0 throughput, 1 latency (four warps per chain), 2 dense throughput, 3 grouped latency
 
-static int run_pose(const stacb_tree *t, const PoseArgs &a, cudaStream_t s) {
+static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
   CUDA_TRY(cudaSetDevice(t->device));
-  CUDA_TRY(cudaMemsetAsync(t->counter, 0, sizeof(int), s));
+  a.counter = t->counter + (t->next.fetch_add(1) % kCounterPool);  // the handle stays logically immutable: each launch owns a counter
+  CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
   // Few chains: latency mode, one CTA of four cooperating warps per chain (speculative line search, see solve4).

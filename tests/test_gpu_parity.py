@@ -405,3 +405,26 @@ def test_fly_tethered_config_against_live_oracle(engine_of):
     np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
     np.testing.assert_allclose(npy(out["sites"]), ref["sites"], atol=MARKER_TOL, rtol=0)
     assert np.array_equal(npy(out["qpos"]), ref["qpos"])
+
+
+def test_concurrent_launches_on_two_streams(rodent, engine_of):
+    """Entry points are re-entrant: two launches of the same tree handle overlapping on different streams."""
+    eng = engine_of(rodent)
+    s = rodent.setup
+    kp, _, _ = rodent.session(2 * 20 * 6, 6, seed=55)
+    kp = kp.reshape(2, 20, 6, -1)
+    base = []
+    for i in range(2):
+        qio = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (20, 1)), device=eng.device)
+        base.append(npy(eng.pose_clips(kp[i], qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())["qpos"]).copy())
+    streams = [torch.cuda.Stream(device=eng.device) for _ in range(2)]
+    kpd = [torch.tensor(kp[i], device=eng.device) for i in range(2)]
+    qios = [torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (20, 1)), device=eng.device) for _ in range(2)]
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(2):
+        with torch.cuda.stream(streams[i]):
+            outs.append(eng.pose_clips(kpd[i], qios[i], s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw()))
+    torch.cuda.synchronize()
+    for i in range(2):
+        np.testing.assert_array_equal(npy(outs[i]["qpos"]), base[i])
