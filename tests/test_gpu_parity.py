@@ -428,3 +428,31 @@ def test_concurrent_launches_on_two_streams(rodent, engine_of):
     torch.cuda.synchronize()
     for i in range(2):
         np.testing.assert_array_equal(npy(outs[i]["qpos"]), base[i])
+
+
+def test_large_batches_use_the_multi_warp_cta_path(rodent, engine_of):
+    """B > 2 x SM count: four independent items per CTA in the batch kernel (fk / loss_grad / q_opt / m_stats)."""
+    eng = engine_of(rodent)
+    s, o = rodent.setup, rodent.oracle(np.float32, 1)
+    B = 700
+    kp, qtrue, _ = rodent.session(B, B, seed=66)
+    q = (qtrue + np.random.default_rng(0).normal(scale=0.02, size=qtrue.shape)).astype(np.float32)
+    qo, xp, xq, sx = [npy(t) for t in eng.fk(q, s.initial_offsets)]
+    qm, km = np.ones(rodent.tree.nq, bool), np.ones(3 * rodent.K, bool)
+    L, G = [npy(t) for t in eng.loss_grad(q, q, kp, qm, km, s.initial_offsets)]
+    st, z2 = eng.m_stats(kp, q)
+    for i in (0, 1, 255, 256, 511, 699):
+        r = o.fk(q[i], s.initial_offsets)
+        np.testing.assert_array_equal(xp[i], r[1])
+        np.testing.assert_array_equal(sx[i], r[3])
+        l, g = o.loss_grad(q[i], q[i], qm, kp[i], km, s.initial_offsets)
+        assert float(l) == float(L[i])
+        np.testing.assert_array_equal(G[i], g)
+    so, z2o = o.m_stats(kp, q)
+    np.testing.assert_array_equal(npy(st), so)
+    assert float(npy(z2)[0]) == float(z2o)
+    p, e, it, ls = [npy(t) for t in eng.q_opt(q[:600], kp[:600], qm, km, s.initial_offsets, s.lb, s.ub, 1e-4, maxiter=5)]
+    for i in (0, 300, 599):
+        po, eo, ito, lso = o.q_opt(q[i], s.lb, s.ub, qm, kp[i], km, s.initial_offsets, 1e-4, maxiter=5)
+        np.testing.assert_array_equal(p[i], po)
+        assert (it[i], ls[i]) == (ito, lso)
