@@ -81,9 +81,8 @@ def offset_optimization(stac_core_obj, mjx_model, mjx_data, kp_data, offsets, q,
     """Closed-form marker offsets from sampled frames (reference ``compute_stac.py:107-167``).
 
     The reference samples with ``jax.random.permutation(PRNGKey(0), arange(F))[:n_sample_frames]``
-    (``:136-140``).  That threefry stream is reproduced when ``jax`` is importable; otherwise pass
-    ``time_indices`` explicitly.  When ``n_sample_frames >= F`` every frame is used and the closed
-    form does not depend on the order.
+    (``:136-140``); `sample_time_indices` reproduces that threefry permutation in numpy.  ``time_indices`` injects an
+    explicit sample (a rank's share of it in multi-GPU fits).
     """
     F = int(kp_data.shape[0])
     if time_indices is None:
@@ -108,18 +107,17 @@ def offset_optimization(stac_core_obj, mjx_model, mjx_data, kp_data, offsets, q,
     return mjx_model, mjx_data, offset_opt_param
 
 
-def sample_time_indices(n_frames: int, n_sample_frames: int) -> np.ndarray:
-    """Frame sample of the m-phase (reference ``compute_stac.py:134-140``)."""
-    try:
-        import jax
+def sample_time_indices(n_frames: int, n_sample_frames: int, partitionable: bool = True) -> np.ndarray:
+    """Frame sample of the m-phase (reference ``compute_stac.py:134-140``):
+    ``jax.random.permutation(jax.random.PRNGKey(0), arange(F), independent=True)[:n_sample]``.
 
-        key = jax.random.PRNGKey(0)
-        return np.asarray(jax.random.permutation(key, jax.numpy.arange(n_frames), independent=True)[:n_sample_frames])
-    except ImportError:
-        if n_sample_frames >= n_frames:
-            return np.arange(n_frames)
-        # documented deviation: without jax the threefry permutation is not reproducible
-        return np.random.default_rng(0).permutation(n_frames)[:n_sample_frames]
+    Reproduced without JAX by ``jax_random`` (threefry2x32 + sort-based shuffle, integer arithmetic only), so the
+    fitted offsets use the frames the reference would use; ``partitionable`` is the ``jax_threefry_partitionable``
+    flag (default of the JAX versions the reference requires).
+    """
+    from . import jax_random
+
+    return jax_random.permutation(0, int(n_frames), partitionable)[: int(n_sample_frames)]
 
 
 def pose_optimization(stac_core_obj, mjx_model, mjx_data, kp_data, lb, ub, site_idxs, indiv_parts):

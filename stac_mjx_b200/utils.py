@@ -31,8 +31,16 @@ def batch_kp_data(kp_data: np.ndarray, n_frames_per_clip: int, continuous: bool 
 
 
 def make_qs(q0, qs_to_opt, q):
-    """``(1 - mask) * q0 + mask * q`` (reference ``utils.py:129-144``); numpy or torch."""
-    return (1 - qs_to_opt) * q0 + qs_to_opt * q
+    """``(1 - mask) * q0 + mask * q`` (reference ``utils.py:129-144``) as a select, for numpy or torch operands
+    in any mix (bool or 0/1 mask); identical to the arithmetic form for finite values."""
+    import torch
+
+    if isinstance(q0, torch.Tensor) or isinstance(q, torch.Tensor):
+        ref = q if isinstance(q, torch.Tensor) else q0
+        as_t = lambda a, dt: a.to(device=ref.device, dtype=dt) if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a), device=ref.device).to(dt)
+        return torch.where(as_t(qs_to_opt, torch.bool), as_t(q, ref.dtype), as_t(q0, ref.dtype))
+    mask = np.asarray(qs_to_opt.cpu() if isinstance(qs_to_opt, torch.Tensor) else qs_to_opt).astype(bool)
+    return np.where(mask, np.asarray(q), np.asarray(q0))
 
 
 def get_site_xpos(data, site_idxs=None):

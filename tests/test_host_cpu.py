@@ -241,3 +241,43 @@ def test_velocity_no_freejoint_reference_case():
     np.testing.assert_allclose(v[0], [1, 2, 3])
     np.testing.assert_allclose(v[1], [1, 2, 3])
     np.testing.assert_allclose(v[2], [0, 0, 0])
+
+
+def test_threefry_known_answers_and_jax_permutation():
+    """jax.random.permutation(PRNGKey(0), arange(F)) restated in numpy (reference compute_stac.py:136-140).
+
+    Pins: the three Random123 known-answer vectors for threefry2x32_20 (also JAX's own prng test) and the published
+    value of jax.random.split(PRNGKey(0)) under the original key derivation."""
+    from stac_mjx_b200 import jax_random as jr
+
+    kat = [((0, 0), (0, 0), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]  # fmt: skip
+    for key, ctr, want in kat:
+        a, b = jr.threefry2x32(key, [ctr[0]], [ctr[1]])
+        assert (int(a[0]), int(b[0])) == want
+    assert jr.prng_key(0) == (0, 0) and jr.prng_key((5 << 32) | 7) == (5, 7)
+    assert jr.split((0, 0), 2, partitionable=False) == [(4146024105, 967050713), (2718843009, 1272950319)]
+    assert jr.split((0, 0), 2, partitionable=True) == [(1797259609, 2579123966), (928981903, 3453687069)]
+    for n in (1, 2, 10, 1000, 2000):  # 2000 needs two sort rounds (ceil(3 ln n / ln(2^32-1)))
+        for part in (True, False):
+            p = jr.permutation(0, n, part)
+            assert sorted(p.tolist()) == list(range(n))
+    # the config-3 sample (1000 fit frames, N_SAMPLE_FRAMES=100): fixed forever, integer arithmetic only
+    idx = compute_stac.sample_time_indices(1000, 100)
+    assert idx[:10].tolist() == [166, 872, 474, 336, 210, 769, 0, 475, 36, 835]
+    assert len(set(idx.tolist())) == 100
+
+
+def test_make_qs_accepts_torch_and_numpy_in_any_mix():
+    import torch
+
+    q0, q = np.arange(5, dtype=np.float32), -np.ones(5, dtype=np.float32)
+    m = np.array([1, 0, 1, 0, 0], bool)
+    want = np.where(m, q, q0)
+    assert np.array_equal(utils.make_qs(q0, m, q), want)
+    assert np.array_equal(utils.make_qs(q0, m.astype(np.float32), q), want)
+    for mm in (m, torch.from_numpy(m), torch.from_numpy(m.astype(np.float32))):
+        for a, b in ((torch.from_numpy(q0), torch.from_numpy(q)), (q0, torch.from_numpy(q)), (torch.from_numpy(q0), q)):
+            out = utils.make_qs(a, mm, b)
+            assert isinstance(out, torch.Tensor) and np.array_equal(out.numpy(), want)
