@@ -1,0 +1,476 @@
+// stacb_fast.cuh -- the register-resident solver for hinge trees (sm_100a): the hot path of libstacb.so.
+//
+// Applies to models whose ACTIVE subtree (ancestors of the marker bodies) has at most 31 bodies, at most 31 marker sites,
+// hinge joints only plus (optionally) one free joint on a top-level body: the rodent / rat23 and C. elegans models of the
+// reference.  Everything else takes the general kernels of stacb_device.cuh.
+//
+// Mapping (fixed for the whole kernel, all state in registers, no shared memory inside an evaluation):
+//   lane e  <->  active body e (set order = body id order, parents first); lane 31 (and every lane >= n) is an IDENTITY
+//               element, so "no ancestor" needs no select: composing with the identity is exact;
+//   lane p  <->  marker site at sorted position p (sites sorted by body id, so a subtree is a contiguous range);
+//   solver  <->  slot j < JM of a lane is the angle of hinge j of the lane's body, slot JM of lanes 0..6 holds the seven
+//               coordinates of the free joint.  Coordinates of the model that are not in this layout ("passive": hinges
+//               outside the active subtree) have an identically zero gradient and never move (see solve).
+//
+// Canonical arithmetic of this path ("fast order", mirrored op for op by oracle/stac_oracle.c mode 2):
+//   * first hinge of a body folded with the body's constant pose: quat = Qc cos(h) + Qs sin(h), pos = A + B cos(t) + C sin(t),
+//     h = (q - ref)/2, cos t = cos^2 h - sin^2 h, sin t = 2 sin h cos h  (Qc, Qs, A, B, C derived once per lane);
+//   * further hinges of the same body composed in the parent frame: quat' = quat * ql, pos' = pos + R(quat)(jperp (1 - cos t) - (a x jpos) sin t);
+//   * world quaternions by pointer jumping (round r composes with the ancestor at distance 2^r), then ONE rotation of every local
+//     offset by its parent's world quaternion and pointer jumping with plain additions for the world positions;
+//   * rotate(v, q) = v + 2 (s t + u x t), t = u x v;
+//   * residuals, loss butterfly, wrench prefix scan and parent-frame Jacobian transpose as in DESIGN.md section 4.
+// Replaces reference stac_mjx/stac_core.py:27-99 and the MJX / jaxopt code under it (see stacb_device.cuh for the citations).
+#pragma once
+#include "stacb_device.cuh"
+
+namespace stacb {
+namespace fast {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int IDL = 31;  // identity lane
+
+// v + 2 (s (u x v) + u x (u x v)): rotation of v by the (unit) quaternion q = (s, u)
+__device__ __forceinline__ V3 rotq(V3 v, Q4 q) {
+  const V3 u = mk3(q.x, q.y, q.z);
+  const V3 t = cross3(u, v);
+  const V3 c = cross3(u, t);
+  const V3 w = mk3(fmaf(q.w, t.x, c.x), fmaf(q.w, t.y, c.y), fmaf(q.w, t.z, c.z));
+  return mk3(fmaf(2.0f, w.x, v.x), fmaf(2.0f, w.y, v.y), fmaf(2.0f, w.z, v.z));
+}
+__device__ __forceinline__ Q4 conj4(Q4 q) { return mk4(q.w, -q.x, -q.y, -q.z); }
+
+template <int JM, int RT>
+struct LaneC {
+  Q4 Qc, Qs;            // first hinge folded with the body's constant pose
+  V3 A, B, C;
+  V3 anc[JM], ax[JM];   // slot 0: constant parent-frame anchor / axis of the first hinge (slots >= 1 live in Fwd)
+  V3 jax[JM], jpp[JM], jcx[JM], jps[JM];  // slots >= 1: axis, jpos - a (a.jpos), a x jpos, jpos (body frame)
+  float ref[JM];
+  int adr[JM];          // qpos address of the hinge in slot j (0 when the slot is empty)
+  bool hinge[JM];
+  bool pfree;           // the lane's body carries the primary free joint
+  int src[RT];          // lane of the ancestor at distance 2^r (IDL when there is none)
+  int par;              // lane of the parent (IDL for a top-level body)
+  int sa, se;           // sorted-site range below the body (0, 0 when nothing to differentiate)
+};
+
+struct SiteC {
+  int k;       // keypoint index of the site at sorted position `lane`, -1 if none
+  int eb;      // lane of the site's body
+  V3 off, kp, km;
+};
+
+template <int JM>
+struct Fwd {
+  V3 P; Q4 Q;          // world pose of the lane's body
+  Q4 Qp;               // world quaternion of its parent
+  V3 anc[JM], ax[JM];  // parent-frame anchor / axis of hinge slots >= 1 (slot 0 is a lane constant)
+  V3 s, res;           // marker site position and masked residual (site lanes)
+  V3 fpos; Q4 fq; float frinv;  // free joint: position, normalised quaternion, reciprocal of the normalisation divisor
+};
+
+template <int JM, int RT>
+__device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, int lane) {
+  const DevSet &S = T.act;
+  const bool on = lane < S.n;
+  BodyConst b;
+  load_body(b, S.rec + (size_t)(on ? lane : 0) * REC);
+  if (!on) { b.nj = 0; b.parent = -1; b.pos = mk3(0.f, 0.f, 0.f); b.quat = mk4(1.f, 0.f, 0.f, 0.f); }
+  L.pfree = on && lane == T.free_e;
+  V3 a0 = mk3(0.f, 0.f, 0.f), p0 = mk3(0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < JM; j++) {
+    const bool h = on && j < b.nj && b.jtype[j] == STACB_JNT_HINGE;
+    L.hinge[j] = h;
+    L.adr[j] = h ? b.jadr[j] : 0;
+    L.ref[j] = h ? b.jref[j] : 0.f;
+    const V3 a = h ? b.jaxis[j] : mk3(0.f, 0.f, 0.f), jp = h ? b.jpos[j] : mk3(0.f, 0.f, 0.f);
+    if (j == 0) { a0 = a; p0 = jp; }
+    const float da = dot3(a, jp);
+    L.jax[j] = a;
+    L.jps[j] = jp;
+    L.jpp[j] = sub3(jp, mk3(a.x * da, a.y * da, a.z * da));
+    L.jcx[j] = cross3(a, jp);
+    L.anc[j] = mk3(0.f, 0.f, 0.f);
+    L.ax[j] = mk3(0.f, 0.f, 0.f);
+  }
+  L.Qc = b.quat;
+  L.Qs = qmul(b.quat, mk4(0.f, a0.x, a0.y, a0.z));
+  const V3 rb = rotq(L.jpp[0], b.quat), rc = rotq(L.jcx[0], b.quat);
+  L.A = add3(b.pos, rb);
+  L.B = mk3(-rb.x, -rb.y, -rb.z);
+  L.C = mk3(-rc.x, -rc.y, -rc.z);
+  L.anc[0] = add3(rotq(p0, b.quat), b.pos);
+  L.ax[0] = rotq(a0, b.quat);
+#pragma unroll
+  for (int r = 0; r < RT; r++) {
+    int a = lane >= S.n ? lane : IDL;
+    if (on && r < S.rounds) { const int t = __ldg(S.anc + r * S.n + lane); if (t >= 0) a = t; }
+    L.src[r] = a;
+  }
+  L.par = on ? (b.parent >= 0 ? b.parent : IDL) : lane;
+  const bool live = on && b.nj > 0 && b.jse[0] > b.jsa[0];
+  L.sa = live ? b.jsa[0] : 0;
+  L.se = live ? b.jse[0] : 0;
+}
+
+__device__ __forceinline__ void site_init(SiteC &st, const DevTree &T, int lane, const float *__restrict__ site_pos) {
+  st.k = -1; st.eb = IDL;
+  st.off = mk3(0.f, 0.f, 0.f); st.kp = mk3(0.f, 0.f, 0.f); st.km = mk3(0.f, 0.f, 0.f);
+  if (lane < T.K) {
+    st.k = __ldg(T.site_order + lane);
+    st.eb = __ldg(T.site_eact + lane);
+    if (site_pos) st.off = mk3(__ldg(site_pos + 3 * st.k), __ldg(site_pos + 3 * st.k + 1), __ldg(site_pos + 3 * st.k + 2));
+  }
+}
+__device__ __forceinline__ void site_load_kp(SiteC &st, const float *__restrict__ kp) {
+  if (st.k >= 0) st.kp = mk3(kp[3 * st.k], kp[3 * st.k + 1], kp[3 * st.k + 2]);
+}
+__device__ __forceinline__ void site_mask_u8(SiteC &st, const uint8_t *__restrict__ m3 /*[3K] or null = ones*/) {
+  if (st.k >= 0) st.km = m3 ? mk3(m3[3 * st.k] ? 1.f : 0.f, m3[3 * st.k + 1] ? 1.f : 0.f, m3[3 * st.k + 2] ? 1.f : 0.f) : mk3(1.f, 1.f, 1.f);
+}
+__device__ __forceinline__ void site_mask_kp(SiteC &st, const uint8_t *__restrict__ per_kp /*[K] or null = ones*/) {
+  if (st.k >= 0) { const float m = (!per_kp || per_kp[st.k]) ? 1.f : 0.f; st.km = mk3(m, m, m); }
+}
+
+// Forward half of q_loss (stac_core.py:27-63) at the point `pt` (solver layout, already merged with q0 by make_qs).
+// RT = pointer-jumping rounds of the kernel variant (>= ceil(log2(depth)); surplus rounds compose with the identity).
+template <int JM, int RT, bool KEEP>
+__device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &st, bool has_free, const float (&pt)[JM + 1], Fwd<JM> &S) {
+  // free joint: every lane normalises the same seven values (broadcast from lanes 0..6)
+  if (has_free) {
+    float fr[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) fr[i] = __shfl_sync(FULL, pt[JM], i);
+    S.fpos = mk3(fr[0], fr[1], fr[2]);
+    S.fq = normalize4(mk4(fr[3], fr[4], fr[5], fr[6]), &S.frinv);
+  } else {
+    S.fpos = mk3(0.f, 0.f, 0.f); S.fq = mk4(1.f, 0.f, 0.f, 0.f); S.frinv = 1.f;
+  }
+  float sh[JM], ch[JM];
+#pragma unroll
+  for (int j = 0; j < JM; j++) sincos_canon((pt[j] - L.ref[j]) * 0.5f, &sh[j], &ch[j]);
+  // first hinge, folded with the body's constant pose
+  float ct = fmaf(ch[0], ch[0], -(sh[0] * sh[0])), sn = 2.0f * (sh[0] * ch[0]);
+  Q4 quat = mk4(fmaf(L.Qs.w, sh[0], L.Qc.w * ch[0]), fmaf(L.Qs.x, sh[0], L.Qc.x * ch[0]), fmaf(L.Qs.y, sh[0], L.Qc.y * ch[0]),
+                fmaf(L.Qs.z, sh[0], L.Qc.z * ch[0]));
+  V3 pos = mk3(fmaf(L.C.x, sn, fmaf(L.B.x, ct, L.A.x)), fmaf(L.C.y, sn, fmaf(L.B.y, ct, L.A.y)), fmaf(L.C.z, sn, fmaf(L.B.z, ct, L.A.z)));
+  pos = sel3(L.pfree, S.fpos, pos);
+  quat = sel4(L.pfree, S.fq, quat);
+#pragma unroll
+  for (int j = 1; j < JM; j++) {  // further hinges of the same body
+    if (KEEP) { S.anc[j] = add3(pos, rotq(L.jps[j], quat)); S.ax[j] = rotq(L.jax[j], quat); }
+    ct = fmaf(ch[j], ch[j], -(sh[j] * sh[j]));
+    sn = 2.0f * (sh[j] * ch[j]);
+    const float om = 1.0f - ct;
+    const V3 pl = mk3(fmaf(-L.jcx[j].x, sn, L.jpp[j].x * om), fmaf(-L.jcx[j].y, sn, L.jpp[j].y * om), fmaf(-L.jcx[j].z, sn, L.jpp[j].z * om));
+    pos = add3(pos, rotq(pl, quat));
+    quat = qmul(quat, mk4(ch[j], L.jax[j].x * sh[j], L.jax[j].y * sh[j], L.jax[j].z * sh[j]));
+  }
+  // world quaternions: pointer jumping
+  Q4 Q = quat;
+#pragma unroll
+  for (int r = 0; r < RT; r++) Q = qmul(shfl4(Q, L.src[r]), Q);
+  // world positions: rotate the local offset by the parent's world quaternion, then pointer jumping with additions
+  S.Qp = shfl4(Q, L.par);
+  V3 v = rotq(pos, S.Qp);
+#pragma unroll
+  for (int r = 0; r < RT; r++) v = add3(shfl3(v, L.src[r]), v);
+  S.P = v;
+  S.Q = Q;
+  // marker sites, masked residuals, loss
+  const V3 pb = shfl3(v, st.eb);
+  const Q4 qb = shfl4(Q, st.eb);
+  S.s = add3(pb, rotq(st.off, qb));
+  S.res = mk3((st.kp.x - S.s.x) * st.km.x, (st.kp.y - S.s.y) * st.km.y, (st.kp.z - S.s.z) * st.km.z);
+  return warp_sum(fmaf(S.res.z, S.res.z, fmaf(S.res.y, S.res.y, S.res.x * S.res.x)));
+}
+
+// Reverse half: d loss / d (solver slots) at the point of the last eval_fwd<KEEP = true>.
+//   free_wanted: some coordinate of the free joint is optimised (uniform); free_sa / free_se: its sorted-site range.
+template <int JM, int RT>
+__device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &S, int lane, bool free_wanted, int free_sa, int free_se,
+                                         float (&g)[JM + 1]) {
+  const V3 c = shfl3(S.P, 0);
+  const V3 f = mk3(-2.0f * S.res.x, -2.0f * S.res.y, -2.0f * S.res.z);
+  const V3 tq = cross3(sub3(S.s, c), f);
+  float w[6] = {f.x, f.y, f.z, tq.x, tq.y, tq.z};
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const float up = __shfl_up_sync(FULL, w[i], off);
+      if (lane >= off) w[i] = w[i] + up;
+    }
+  }
+  float ex[6], wr[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float up = __shfl_up_sync(FULL, w[i], 1);
+    ex[i] = lane >= 1 ? up : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) wr[i] = __shfl_sync(FULL, ex[i], L.se) - __shfl_sync(FULL, ex[i], L.sa);
+  const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
+  // the subtree wrench in the parent frame of the body, then every hinge slot of the body
+  const V3 pp = shfl3(S.P, L.par);
+  const Q4 pc = conj4(S.Qp);
+  const V3 T0 = sub3(Tq, cross3(sub3(pp, c), F));
+  const V3 Fp = rotq(F, pc), Tp = rotq(T0, pc);
+  g[0] = dot3(L.ax[0], sub3(Tp, cross3(L.anc[0], Fp)));
+#pragma unroll
+  for (int j = 1; j < JM; j++) g[j] = dot3(S.ax[j], sub3(Tp, cross3(S.anc[j], Fp)));
+  g[JM] = 0.f;
+  if (free_wanted) {  // uniform
+    float wf[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) wf[i] = __shfl_sync(FULL, ex[i], free_se) - __shfl_sync(FULL, ex[i], free_sa);
+    const V3 Ff = mk3(wf[0], wf[1], wf[2]);
+    const V3 Tf = sub3(mk3(wf[3], wf[4], wf[5]), cross3(sub3(S.fpos, c), Ff));
+    float g4[4];
+    quat_grad_left(S.fq, Tf, S.frinv, g4);
+    float v = Ff.x;
+    v = lane == 1 ? Ff.y : v; v = lane == 2 ? Ff.z : v; v = lane == 3 ? g4[0] : v;
+    v = lane == 4 ? g4[1] : v; v = lane == 5 ? g4[2] : v; v = lane == 6 ? g4[3] : v;
+    g[JM] = lane < 7 ? v : 0.f;
+  }
+}
+
+// Solver-side lane state.
+template <int NS>
+struct Slots {
+  float lb[NS], ub[NS];
+  bool valid[NS];
+};
+
+template <int NS>
+__device__ __forceinline__ float lane_dot(const float (&a)[NS], const float (&b)[NS]) {
+  float acc = a[0] * b[0];
+#pragma unroll
+  for (int m = 1; m < NS; m++) acc = fmaf(a[m], b[m], acc);
+  return acc;
+}
+
+__device__ __forceinline__ void warp_sum2(float &a, float &b) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float ta = __shfl_xor_sync(FULL, a, off), tb = __shfl_xor_sync(FULL, b, off);
+    a = a + ta;
+    b = b + tb;
+  }
+}
+
+// Per-kernel constants every evaluation needs (registers).
+struct Uni {
+  int lane, free_sa, free_se;
+  bool has_free;
+  float tol;
+  int maxiter, maxls;
+};
+
+template <int JM>
+__device__ __forceinline__ bool free_wanted_of(const Uni &u, unsigned maskbits) {
+  return u.has_free && __any_sync(FULL, u.lane < 7 && ((maskbits >> JM) & 1u));
+}
+
+// ------------------------------------------------------------------------------------------
+// jaxopt 0.8.5 ProjectedGradient.run (ProximalGradient._update_accel / _ls / _error with the box projection), one warp.
+// Two-state machine so the kernel holds ONE forward and ONE reverse evaluation:
+//   state Y : the point is the FISTA extrapolation y -> loss + gradient, then the first line-search candidate
+//   state LS: the point is a candidate x+ -> loss; rejected: halve the step; accepted: gradient at x+ from the state of
+//             this same evaluation (the reference recomputes FK there: same values), error, next y.
+//   sqp: squared distance the projection moves the PASSIVE coordinates in the first iteration (they have zero gradient:
+//        x+ = clip(q0) from then on; zero whenever q0 is inside the box).
+// ------------------------------------------------------------------------------------------
+template <int JM, int RT>
+__device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &st, const Uni &u, const Slots<JM + 1> &co, const float (&q0)[JM + 1],
+                                          unsigned maskbits, float sqp, float (&x)[JM + 1]) {
+  constexpr int NS = JM + 1;
+  float y[NS], g[NS], xn[NS], d[NS], gt[NS];
+#pragma unroll
+  for (int m = 0; m < NS; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; xn[m] = x[m]; g[m] = 0.f; gt[m] = 0.f; }
+  float t = 1.0f, step = 1.0f, stp = 1.0f, fy = 0.f, sq = 0.f, dg = 0.f;
+  int halv = 0;
+  bool in_ls = false;
+  SolveOut out;
+  out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
+  if (u.maxiter <= 0) return out;
+  const bool fw = free_wanted_of<JM>(u, maskbits);
+  Fwd<JM> S;
+  for (;;) {
+    float pt[NS];
+#pragma unroll
+    for (int m = 0; m < NS; m++) pt[m] = ((maskbits >> m) & 1u) ? (in_ls ? xn[m] : y[m]) : q0[m];
+    const float f = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+    bool rejected = false;
+    if (in_ls) {
+      out.ls++;
+      if (!(f - f == 0.0f)) out.bad = true;
+      const float dec = stp * (f - fy);
+      const float cond = fmaf(stp, dg, 0.5f * sq);
+      rejected = (dec > cond + 1.1920929e-07f) && (halv < u.maxls);
+    }
+    if (!rejected) {
+      eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_sa, u.free_se, gt);
+#pragma unroll
+      for (int m = 0; m < NS; m++) gt[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? gt[m] : 0.f;
+      if (in_ls) {  // accepted x+ = xn
+        step = (stp <= 1e-6f) ? 1.0f : stp / 0.5f;
+        const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+        const float beta = (t - 1.0f) / tn;
+#pragma unroll
+        for (int m = 0; m < NS; m++) {
+          y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
+          d[m] = co.valid[m] ? clipf(xn[m] - gt[m], co.lb[m], co.ub[m]) - xn[m] : 0.f;
+          x[m] = xn[m];
+        }
+        out.err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
+        t = tn;
+        out.iters++;
+        sqp = 0.f;
+        if (!(out.err > u.tol && out.iters < u.maxiter)) break;
+        in_ls = false;
+        continue;
+      }
+      fy = f;
+#pragma unroll
+      for (int m = 0; m < NS; m++) g[m] = gt[m];
+      stp = step;
+      halv = 0;
+      in_ls = true;
+    } else {
+      stp = stp * 0.5f;
+      halv++;
+    }
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+      xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      d[m] = xn[m] - y[m];
+    }
+    sq = lane_dot<NS>(d, d);
+    dg = lane_dot<NS>(d, g);
+    warp_sum2(sq, dg);
+    sq = sq + sqp;
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// Latency mode: 2 * NC warps cooperate on ONE chain.  Per FISTA iteration warp j < NC evaluates the line-search candidate
+// x+_j (step s / 2^j) and the gradient there (stopping criterion), warp NC + j evaluates the extrapolation y'(x+_j) and the
+// gradient there (next iteration); ONE block barrier per round, results exchanged through a double-buffered shared area.
+// The accepted candidate is the first one the sequential line search would accept and every evaluation is the same
+// arithmetic as in `solve`, so results are bit-identical to the one-warp solver.
+// ------------------------------------------------------------------------------------------
+template <int NS, int NC>
+struct Xchg {  // shared memory
+  float g[2][NC][32 * NS];
+  float acc[2][NC], err[2][NC], fy[2][NC];
+  float bad;
+};
+
+template <int JM, int RT, int NC>
+__device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const SiteC &st, const Uni &u, const Slots<JM + 1> &co, const float (&q0)[JM + 1],
+                                               unsigned maskbits, float sqp, float (&x)[JM + 1], Xchg<JM + 1, NC> *xc, int w, int &par) {
+  constexpr int NS = JM + 1;
+  float y[NS], g[NS], gt[NS], xj[NS], pt[NS], d[NS];
+#pragma unroll
+  for (int m = 0; m < NS; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; g[m] = 0.f; }
+  SolveOut out;
+  out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
+  if (u.maxiter <= 0) return out;
+  const bool fw = free_wanted_of<JM>(u, maskbits);
+  const int j = w % NC;
+  const bool isY = w >= NC;
+  Fwd<JM> S;
+  // f(y0), grad f(y0): every warp computes them (identical values)
+#pragma unroll
+  for (int m = 0; m < NS; m++) pt[m] = ((maskbits >> m) & 1u) ? y[m] : q0[m];
+  float fy = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+  eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_sa, u.free_se, g);
+#pragma unroll
+  for (int m = 0; m < NS; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? g[m] : 0.f;
+  float t = 1.0f, stp = 1.0f;
+  float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+  float beta = (t - 1.0f) / tn;
+  int base = 0;
+  for (;;) {
+    float sj = stp;
+#pragma unroll
+    for (int i = 0; i < NC - 1; i++) sj = (i < j) ? sj * 0.5f : sj;
+    float sq = 0.f, dg = 0.f;
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+      xj[m] = co.valid[m] ? clipf(fmaf(-sj, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      d[m] = xj[m] - y[m];
+      const float p = isY ? fmaf(beta, xj[m] - x[m], xj[m]) : xj[m];
+      pt[m] = ((maskbits >> m) & 1u) ? p : q0[m];
+    }
+    if (!isY) {
+      sq = lane_dot<NS>(d, d);
+      dg = lane_dot<NS>(d, g);
+      warp_sum2(sq, dg);
+      sq = sq + sqp;
+    }
+    const float f = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+    eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_sa, u.free_se, gt);
+#pragma unroll
+    for (int m = 0; m < NS; m++) gt[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? gt[m] : 0.f;
+    if (!isY) {
+      const float dec = sj * (f - fy);
+      const float cond = fmaf(sj, dg, 0.5f * sq);
+      const bool rejected = (dec > cond + 1.1920929e-07f) && (base + j < u.maxls);
+#pragma unroll
+      for (int m = 0; m < NS; m++) d[m] = co.valid[m] ? clipf(xj[m] - gt[m], co.lb[m], co.ub[m]) - xj[m] : 0.f;
+      const float err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
+      if (u.lane == 0) {
+        xc->acc[par][j] = rejected ? 0.f : 1.f;
+        xc->err[par][j] = err;
+        if (!(f - f == 0.0f)) xc->bad = 1.f;
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NS; m++) xc->g[par][j][32 * m + u.lane] = gt[m];
+      if (u.lane == 0) xc->fy[par][j] = f;
+    }
+    __syncthreads();
+    int k = -1;
+#pragma unroll
+    for (int i = NC - 1; i >= 0; i--) k = (xc->acc[par][i] != 0.f) ? i : k;
+    const int rp = par;
+    par ^= 1;
+    if (k < 0) {  // every candidate rejected: next NC step sizes
+      base += NC;
+#pragma unroll
+      for (int i = 0; i < NC; i++) stp = stp * 0.5f;
+      continue;
+    }
+    out.ls += base + k + 1;  // evaluations the sequential line search performs
+    float sk = stp;
+#pragma unroll
+    for (int i = 0; i < NC - 1; i++) sk = (i < k) ? sk * 0.5f : sk;
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+      const float xk = co.valid[m] ? clipf(fmaf(-sk, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      y[m] = fmaf(beta, xk - x[m], xk);
+      x[m] = xk;
+    }
+#pragma unroll
+    for (int m = 0; m < NS; m++) g[m] = xc->g[rp][k][32 * m + u.lane];
+    fy = xc->fy[rp][k];
+    out.err = xc->err[rp][k];
+    t = tn;
+    tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+    beta = (t - 1.0f) / tn;
+    stp = (sk <= 1e-6f) ? 1.0f : sk / 0.5f;
+    out.iters++;
+    sqp = 0.f;
+    if (!(out.err > u.tol && out.iters < u.maxiter)) break;
+    base = 0;
+  }
+  return out;
+}
+
+}  // namespace fast
+}  // namespace stacb

@@ -34,12 +34,13 @@ class StacData:
 
 
 def _config_yaml(config) -> str:
+    plain = config.to_dict() if hasattr(config, "to_dict") else config
     try:
-        from omegaconf import OmegaConf
-
-        return OmegaConf.to_yaml(config)
+        from omegaconf import DictConfig, OmegaConf
     except ImportError:
-        return yaml.safe_dump(config.to_dict() if hasattr(config, "to_dict") else dict(config), sort_keys=False)
+        return yaml.safe_dump(dict(plain), sort_keys=False)
+    # this package's Cfg is a dict subclass, which OmegaConf does not accept as a container: go through a plain dict
+    return OmegaConf.to_yaml(plain if isinstance(plain, DictConfig) else OmegaConf.create(dict(plain)))
 
 
 def save_data_to_h5(config, kp_names, names_qpos, names_xpos, kp_data, marker_sites, offsets, qpos, xpos, xquat, qvel, file_path):
