@@ -22,7 +22,9 @@
  *     passed as void*; NULL = legacy default stream).
  *   - return value: 0 on success, negative on error (STACB_E_*); stacb_last_error()
  *     returns a thread-local message for the last failing call.
- *   - handles are immutable after creation: entry points are re-entrant.
+ *   - no process-global state: compute entry points take a const handle and are re-entrant (up to 64 launches of one
+ *     handle may be in flight at once); the two scheduling knobs (stacb_tree_set_mode / _set_path) live in the handle;
+ *     the caller's current CUDA device is restored before every entry point returns.
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
  *
  * All arithmetic is float32 in a fixed ("canonical") operation order documented in
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define STACB_VERSION 100
+#define STACB_VERSION 200
 
 #define STACB_OK 0
 #define STACB_E_INVALID (-1)     /* bad argument / unsupported model feature */
@@ -128,11 +130,22 @@ int stacb_m_stats(const stacb_tree *tree, const float *kp, const float *q, float
  * (blocks x threads, `iters` iterations of 16 independent FMAs per thread). out [blocks*threads]. */
 int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream);
 
-/* Scheduling of stacb_pose_clips: -1 auto (default), 0 throughput mode (one warp per clip chain),
- * 1 latency mode (four cooperating warps per chain, speculative line search), 2 dense throughput mode (registers
- * capped so 16 chains fit per SM; chosen automatically from 16 chains per SM), 3 grouped latency mode (wide trees: each of
- * the four speculative evaluations is carried out by three warps sharing the bodies). Results are bit-identical. */
-int stacb_set_mode(int mode);
+/* Scheduling of stacb_pose_clips for this handle: -1 auto (default), 0 throughput mode (one warp per clip chain),
+ * 1 latency mode (four cooperating warps per chain, speculative line search), 2 dense throughput mode (registers capped so 16
+ * chains fit per SM; chosen automatically from 16 chains per SM), 3 wide latency mode (register-resident path: six warps per
+ * chain speculating on three line-search candidates; general path: each of the four speculative evaluations carried out by
+ * three warps sharing the bodies of a wide tree).  Results do not depend on the mode (bit-identical).
+ * The setting is a property of the handle, not of the process; do not change it while a launch of the same handle is being
+ * enqueued from another thread. */
+int stacb_tree_set_mode(stacb_tree *tree, int mode);
+
+/* Which kernels serve the handle: 0 (default) = the register-resident hinge-tree solver where the model qualifies (active
+ * subtree of at most 31 bodies with hinge joints plus one free joint, at most 31 keypoint sites: rodent, C. elegans), the
+ * general kernels elsewhere; 1 = general kernels only.  The two paths evaluate the same mathematics in different (each
+ * fixed and documented) float32 operation orders, so their results agree to rounding, not bit for bit.
+ * stacb_tree_path returns 1 when the register-resident solver serves the handle, 0 otherwise. */
+int stacb_tree_set_path(stacb_tree *tree, int path);
+int stacb_tree_path(const stacb_tree *tree);
 
 const char *stacb_last_error(void);
 int stacb_version(void);

@@ -1,0 +1,364 @@
+/*
+ * fast_order.h -- mode 2 ("fast order") of the oracle: the arithmetic of the register-resident hinge-tree solver
+ * (stac_mjx_b200/csrc/stacb_fast.cuh), restated lane by lane in plain C.  Included by stac_oracle.c.
+ *
+ * TEST INFRASTRUCTURE ONLY (see stac_oracle.c).  Same mathematics as modes 0 / 1 (reference stac_mjx/stac_core.py:27-99
+ * over MJX kinematics and jaxopt ProjectedGradient); only the float32 operation order differs:
+ *   - 32 "lanes": lane e < nact is active body e (ascending body id), lane 31 and every lane >= nact is an identity element;
+ *     lane p < K is the marker site at sorted position p; solver slot j < JM of lane e is hinge j of body e, slot JM of
+ *     lanes 0..6 the free joint; every other qpos address is passive (zero gradient);
+ *   - first hinge of a body folded with the body's constant pose (quat = Qc cos h + Qs sin h, pos = A + B cos t + C sin t),
+ *     further hinges composed in the parent frame, world quaternions by pointer jumping, ONE rotation of each local offset by
+ *     the parent's world quaternion, world positions by pointer jumping with plain additions;
+ *   - rotate(v, q) = v + 2 (s t + u x t), t = u x v;
+ *   - one site per lane: loss by the 32-lane butterfly, wrench prefix by Hillis-Steele over lanes;
+ *   - solver reductions: per-lane fma chain over the slots, then the butterfly; the passive coordinates enter the first
+ *     line search through their own lane-dealt sum.
+ * (JM, RT) is the kernel variant the dispatcher picks (first fit of (1,5,1), (3,4,3)): surplus slots / rounds are no-ops
+ * but are executed here as well so that even signed zeros agree.
+ */
+
+#define FJ 3 /* slots a variant can have */
+#define FNS (FJ + 1)
+#define IDL 31
+
+typedef struct {
+  int JM, RT, n, K, has_free, free_adr, free_sa, free_se;
+  q4 Qc[LANES], Qs[LANES];
+  v3 A[LANES], B[LANES], C[LANES], anc0[LANES], ax0[LANES];
+  v3 jax[LANES][FJ], jpp[LANES][FJ], jcx[LANES][FJ], jps[LANES][FJ];
+  REAL ref[LANES][FJ];
+  int hinge[LANES][FJ], pfree[LANES];
+  int src[LANES][8], par[LANES], sa[LANES], se[LANES];
+  int sk[LANES], seb[LANES];             /* sites: keypoint index (-1 none), lane of the body */
+  int valid[LANES][FNS], adr[LANES][FNS]; /* solver slots */
+  int npassive, *passive;
+} ofast;
+
+static inline v3 f_rotq(v3 v, q4 q) {
+  v3 u = { q.x, q.y, q.z };
+  v3 t = c_cross(u, v);
+  v3 c = c_cross(u, t);
+  v3 w = { r_fma(q.w, t.x, c.x), r_fma(q.w, t.y, c.y), r_fma(q.w, t.z, c.z) };
+  v3 r = { r_fma(R(2), w.x, v.x), r_fma(R(2), w.y, v.y), r_fma(R(2), w.z, v.z) };
+  return r;
+}
+
+static void fast_destroy(ofast *F) { if (F) { free(F->passive); free(F); } }
+
+/* NULL when the register-resident path does not serve the model (mirrors stacb_tree_create / fits_fast) */
+static ofast *fast_create(const omodel *m, const osched *s) {
+  int nb = m->nbody, K = m->nsite;
+  if (s->nact > 31 || K > 31) return NULL;
+  int *loc = (int *)calloc(nb, sizeof(int));
+  for (int b = 0; b < nb; b++) loc[b] = -1;
+  for (int e = 0; e < s->nact; e++) loc[s->act[e]] = e;
+  int free_e = -1, free_j = -1, any_other = 0, jm = 1;
+  for (int e = 0; e < s->nact; e++) {
+    int b = s->act[e];
+    if (m->body_jntnum[b] > jm) jm = m->body_jntnum[b];
+    for (int jj = 0; jj < m->body_jntnum[b]; jj++) {
+      int j = m->body_jntadr[b] + jj, t = m->jnt_type[j];
+      if (t == JNT_FREE && free_e < 0 && jj == 0) { free_e = e; free_j = j; }
+      else if (t != JNT_HINGE) any_other = 1;
+    }
+  }
+  int nquat = 0;
+  for (int j = 0; j < m->njnt; j++) if (m->jnt_type[j] == JNT_FREE || m->jnt_type[j] == JNT_BALL) nquat++;
+  int JM = 0, RT = 0, bplf = (s->nfull + 31) / 32;
+  if (jm <= 1 && s->rounds_act <= 5 && bplf <= 1) { JM = 1; RT = 5; }
+  else if (jm <= 3 && s->rounds_act <= 4 && bplf <= 3) { JM = 3; RT = 4; }
+  if (any_other || nquat != (free_e >= 0 ? 1 : 0) || JM == 0) { free(loc); return NULL; }
+  ofast *F = (ofast *)calloc(1, sizeof(ofast));
+  F->JM = JM; F->RT = RT; F->n = s->nact; F->K = K; F->has_free = free_e >= 0;
+  F->free_adr = free_e >= 0 ? m->jnt_qposadr[free_j] : 0;
+  F->free_sa = free_e >= 0 ? s->jnt_s[free_j] : 0; F->free_se = free_e >= 0 ? s->jnt_e[free_j] : 0;
+  char *covered = (char *)calloc(m->nq + 1, 1);
+  for (int l = 0; l < LANES; l++) {
+    int on = l < s->nact, b = on ? s->act[l] : 0;
+    v3 bpos = { 0, 0, 0 }; q4 bquat = { 1, 0, 0, 0 };
+    int nj = 0;
+    if (on) { bpos = ld3(m->body_pos + 3 * b); bquat = ld4(m->body_quat + 4 * b); nj = m->body_jntnum[b]; }
+    F->pfree[l] = on && l == free_e;
+    v3 a0 = { 0, 0, 0 }, p0 = { 0, 0, 0 };
+    for (int jj = 0; jj < JM; jj++) {
+      int j = on && jj < nj ? m->body_jntadr[b] + jj : -1;
+      int h = j >= 0 && m->jnt_type[j] == JNT_HINGE;
+      F->hinge[l][jj] = h;
+      F->valid[l][jj] = h;
+      F->adr[l][jj] = h ? m->jnt_qposadr[j] : 0;
+      F->ref[l][jj] = h ? m->qpos0[m->jnt_qposadr[j]] : R(0);
+      if (h) covered[m->jnt_qposadr[j]] = 1;
+      v3 z = { 0, 0, 0 };
+      v3 a = h ? ld3(m->jnt_axis + 3 * j) : z, jp = h ? ld3(m->jnt_pos + 3 * j) : z;
+      if (jj == 0) { a0 = a; p0 = jp; }
+      REAL da = c_dot3(a, jp);
+      v3 ada = { a.x * da, a.y * da, a.z * da };
+      F->jax[l][jj] = a; F->jps[l][jj] = jp; F->jpp[l][jj] = sub3(jp, ada); F->jcx[l][jj] = c_cross(a, jp);
+    }
+    F->valid[l][JM] = F->has_free && l < 7;
+    F->adr[l][JM] = F->valid[l][JM] ? F->free_adr + l : 0;
+    if (F->valid[l][JM]) covered[F->free_adr + l] = 1;
+    F->Qc[l] = bquat;
+    q4 qa = { 0, a0.x, a0.y, a0.z };
+    F->Qs[l] = c_qmul(bquat, qa);
+    v3 rb = f_rotq(F->jpp[l][0], bquat), rc = f_rotq(F->jcx[l][0], bquat);
+    F->A[l] = add3(bpos, rb);
+    F->B[l].x = -rb.x; F->B[l].y = -rb.y; F->B[l].z = -rb.z;
+    F->C[l].x = -rc.x; F->C[l].y = -rc.y; F->C[l].z = -rc.z;
+    F->anc0[l] = add3(f_rotq(p0, bquat), bpos);
+    F->ax0[l] = f_rotq(a0, bquat);
+    for (int r = 0; r < RT; r++) {
+      int a = l >= s->nact ? l : IDL;
+      if (on && r < s->rounds_act) { int t = s->anc[(size_t)r * nb + b]; if (t >= 0) a = loc[t]; }
+      F->src[l][r] = a;
+    }
+    int p = on ? m->body_parent[b] : 0;
+    F->par[l] = on ? (p != 0 ? loc[p] : IDL) : l;
+    int j0 = on && nj > 0 ? m->body_jntadr[b] : -1;
+    int live = j0 >= 0 && s->jnt_e[j0] > s->jnt_s[j0];
+    F->sa[l] = live ? s->jnt_s[j0] : 0; F->se[l] = live ? s->jnt_e[j0] : 0;
+    F->sk[l] = -1; F->seb[l] = IDL;
+    if (l < K) { F->sk[l] = s->site_order[l]; F->seb[l] = loc[m->site_body[s->site_order[l]]]; }
+  }
+  F->passive = (int *)calloc(m->nq + 1, sizeof(int));
+  for (int i = 0; i < m->nq; i++) if (!covered[i]) F->passive[F->npassive++] = i;
+  free(covered); free(loc);
+  if (F->npassive > 0 && F->passive[0] < 3) { fast_destroy(F); return NULL; }
+  return F;
+}
+
+typedef struct {
+  v3 P[LANES]; q4 Q[LANES], Qp[LANES];
+  v3 anc[LANES][FJ], ax[LANES][FJ];
+  v3 s[LANES], res[LANES];
+  v3 fpos; q4 fq; REAL frinv;
+} ffwd;
+
+/* per-site data in lane order */
+typedef struct { v3 off[LANES], kp[LANES], km[LANES]; } fsites;
+
+static void fast_sites(const ofast *F, const REAL *site_pos, const REAL *kp, const REAL *kpmask, fsites *st) {
+  memset(st, 0, sizeof(*st));
+  for (int l = 0; l < LANES; l++) {
+    int k = F->sk[l];
+    if (k < 0) continue;
+    if (site_pos) st->off[l] = ld3(site_pos + 3 * k);
+    if (kp) st->kp[l] = ld3(kp + 3 * k);
+    if (kpmask) st->km[l] = ld3(kpmask + 3 * k);
+  }
+}
+
+static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd *S) {
+  const int JM = F->JM, RT = F->RT;
+  if (F->has_free) {
+    S->fpos.x = pt[0][JM]; S->fpos.y = pt[1][JM]; S->fpos.z = pt[2][JM];
+    q4 raw = { pt[3][JM], pt[4][JM], pt[5][JM], pt[6][JM] };
+    S->fq = c_normalize4(raw, &S->frinv);
+  } else {
+    S->fpos.x = S->fpos.y = S->fpos.z = R(0); S->fq.w = R(1); S->fq.x = S->fq.y = S->fq.z = R(0); S->frinv = R(1);
+  }
+  q4 Q[LANES], Qn[LANES];
+  v3 lp[LANES];
+  for (int l = 0; l < LANES; l++) {
+    REAL sh[FJ], ch[FJ];
+    for (int j = 0; j < JM; j++) c_sincos((pt[l][j] - F->ref[l][j]) * R(0.5), &sh[j], &ch[j]);
+    REAL ct = r_fma(ch[0], ch[0], -(sh[0] * sh[0])), sn = R(2) * (sh[0] * ch[0]);
+    q4 quat = { r_fma(F->Qs[l].w, sh[0], F->Qc[l].w * ch[0]), r_fma(F->Qs[l].x, sh[0], F->Qc[l].x * ch[0]),
+                r_fma(F->Qs[l].y, sh[0], F->Qc[l].y * ch[0]), r_fma(F->Qs[l].z, sh[0], F->Qc[l].z * ch[0]) };
+    v3 pos = { r_fma(F->C[l].x, sn, r_fma(F->B[l].x, ct, F->A[l].x)), r_fma(F->C[l].y, sn, r_fma(F->B[l].y, ct, F->A[l].y)),
+               r_fma(F->C[l].z, sn, r_fma(F->B[l].z, ct, F->A[l].z)) };
+    if (F->pfree[l]) { pos = S->fpos; quat = S->fq; }
+    for (int j = 1; j < JM; j++) {
+      S->anc[l][j] = add3(pos, f_rotq(F->jps[l][j], quat));
+      S->ax[l][j] = f_rotq(F->jax[l][j], quat);
+      ct = r_fma(ch[j], ch[j], -(sh[j] * sh[j]));
+      sn = R(2) * (sh[j] * ch[j]);
+      REAL om = R(1) - ct;
+      v3 pl = { r_fma(-F->jcx[l][j].x, sn, F->jpp[l][j].x * om), r_fma(-F->jcx[l][j].y, sn, F->jpp[l][j].y * om),
+                r_fma(-F->jcx[l][j].z, sn, F->jpp[l][j].z * om) };
+      pos = add3(pos, f_rotq(pl, quat));
+      q4 ql = { ch[j], F->jax[l][j].x * sh[j], F->jax[l][j].y * sh[j], F->jax[l][j].z * sh[j] };
+      quat = c_qmul(quat, ql);
+    }
+    Q[l] = quat; lp[l] = pos;
+  }
+  for (int r = 0; r < RT; r++) {
+    for (int l = 0; l < LANES; l++) Qn[l] = c_qmul(Q[F->src[l][r]], Q[l]);
+    memcpy(Q, Qn, sizeof(Q));
+  }
+  v3 v[LANES], vn[LANES];
+  for (int l = 0; l < LANES; l++) { S->Qp[l] = Q[F->par[l]]; v[l] = f_rotq(lp[l], S->Qp[l]); }
+  for (int r = 0; r < RT; r++) {
+    for (int l = 0; l < LANES; l++) vn[l] = add3(v[F->src[l][r]], v[l]);
+    memcpy(v, vn, sizeof(v));
+  }
+  REAL part[LANES];
+  for (int l = 0; l < LANES; l++) {
+    S->P[l] = v[l]; S->Q[l] = Q[l];
+  }
+  for (int l = 0; l < LANES; l++) {
+    v3 pb = v[F->seb[l]]; q4 qb = Q[F->seb[l]];
+    S->s[l] = add3(pb, f_rotq(st->off[l], qb));
+    S->res[l].x = (st->kp[l].x - S->s[l].x) * st->km[l].x;
+    S->res[l].y = (st->kp[l].y - S->s[l].y) * st->km[l].y;
+    S->res[l].z = (st->kp[l].z - S->s[l].z) * st->km[l].z;
+    part[l] = r_fma(S->res[l].z, S->res[l].z, r_fma(S->res[l].y, S->res[l].y, S->res[l].x * S->res[l].x));
+  }
+  return butterfly32(part);
+}
+
+static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANES][FNS]) {
+  const int JM = F->JM;
+  v3 c = S->P[0];
+  REAL w[LANES][6], t2[LANES][6], ex[LANES + 1][6];
+  for (int l = 0; l < LANES; l++) {
+    v3 f = { R(-2) * S->res[l].x, R(-2) * S->res[l].y, R(-2) * S->res[l].z };
+    v3 tq = c_cross(sub3(S->s[l], c), f);
+    w[l][0] = f.x; w[l][1] = f.y; w[l][2] = f.z; w[l][3] = tq.x; w[l][4] = tq.y; w[l][5] = tq.z;
+  }
+  for (int off = 1; off < LANES; off <<= 1) {
+    for (int l = 0; l < LANES; l++) for (int i = 0; i < 6; i++) t2[l][i] = (l >= off) ? w[l][i] + w[l - off][i] : w[l][i];
+    memcpy(w, t2, sizeof(w));
+  }
+  for (int i = 0; i < 6; i++) { ex[0][i] = R(0); for (int l = 1; l <= LANES; l++) ex[l][i] = w[l - 1][i]; }
+  for (int l = 0; l < LANES; l++) {
+    REAL wr[6];
+    for (int i = 0; i < 6; i++) wr[i] = ex[F->se[l]][i] - ex[F->sa[l]][i];
+    v3 Fo = { wr[0], wr[1], wr[2] }, Tq = { wr[3], wr[4], wr[5] };
+    v3 pp = S->P[F->par[l]];
+    q4 pc = { S->Qp[l].w, -S->Qp[l].x, -S->Qp[l].y, -S->Qp[l].z };
+    v3 T0 = sub3(Tq, c_cross(sub3(pp, c), Fo));
+    v3 Fp = f_rotq(Fo, pc), Tp = f_rotq(T0, pc);
+    g[l][0] = c_dot3(F->ax0[l], sub3(Tp, c_cross(F->anc0[l], Fp)));
+    for (int j = 1; j < JM; j++) g[l][j] = c_dot3(S->ax[l][j], sub3(Tp, c_cross(S->anc[l][j], Fp)));
+    g[l][JM] = R(0);
+  }
+  if (free_wanted) {
+    REAL wf[6];
+    for (int i = 0; i < 6; i++) wf[i] = ex[F->free_se][i] - ex[F->free_sa][i];
+    v3 Ff = { wf[0], wf[1], wf[2] }, Tw = { wf[3], wf[4], wf[5] };
+    v3 Tf = sub3(Tw, c_cross(sub3(S->fpos, c), Ff));
+    q4 qh = S->fq, tq = { 0, Tf.x, Tf.y, Tf.z };
+    q4 h = c_qmul(tq, qh); h.w *= R(2); h.x *= R(2); h.y *= R(2); h.z *= R(2);
+    REAL pr = r_fma(qh.z, h.z, r_fma(qh.y, h.y, r_fma(qh.x, h.x, qh.w * h.w))), n = S->frinv;
+    REAL g7[7] = { Ff.x, Ff.y, Ff.z, r_fma(-qh.w, pr, h.w) * n, r_fma(-qh.x, pr, h.x) * n, r_fma(-qh.y, pr, h.y) * n, r_fma(-qh.z, pr, h.z) * n };
+    for (int l = 0; l < 7; l++) g[l][JM] = g7[l];
+  }
+}
+
+/* slot layout <-> qpos layout */
+static void fast_gather(const ofast *F, const REAL *q, REAL out[LANES][FNS]) {
+  for (int l = 0; l < LANES; l++) for (int m = 0; m <= F->JM; m++) out[l][m] = F->valid[l][m] ? q[F->adr[l][m]] : R(0);
+}
+static void fast_bits(const ofast *F, const uint8_t *qmask, int bits[LANES][FNS]) {
+  for (int l = 0; l < LANES; l++) for (int m = 0; m <= F->JM; m++) bits[l][m] = F->valid[l][m] && qmask[F->adr[l][m]];
+}
+static int fast_free_wanted(const ofast *F, int bits[LANES][FNS]) {
+  if (!F->has_free) return 0;
+  for (int l = 0; l < 7; l++) if (bits[l][F->JM]) return 1;
+  return 0;
+}
+static REAL fast_lane_dot(int NS, const REAL *a, const REAL *b) {
+  REAL acc = a[0] * b[0];
+  for (int m = 1; m < NS; m++) acc = r_fma(a[m], b[m], acc);
+  return acc;
+}
+static REAL fast_dot(const ofast *F, REAL a[LANES][FNS], REAL b[LANES][FNS]) {
+  REAL part[LANES];
+  for (int l = 0; l < LANES; l++) part[l] = fast_lane_dot(F->JM + 1, a[l], b[l]);
+  return butterfly32(part);
+}
+
+/* q_loss and its gradient in fast order; q, q0, grad in the qpos layout */
+static REAL fast_loss_eval(const omodel *m, const ofast *F, const REAL *q, const REAL *q0, const uint8_t *qmask, const REAL *kp,
+                           const REAL *kpmask, const REAL *site_pos, REAL *grad) {
+  fsites st; ffwd S;
+  fast_sites(F, site_pos, kp, kpmask, &st);
+  REAL qs[LANES][FNS], q0s[LANES][FNS], pt[LANES][FNS], g[LANES][FNS];
+  int bits[LANES][FNS];
+  fast_gather(F, q, qs); fast_gather(F, q0, q0s); fast_bits(F, qmask, bits);
+  for (int l = 0; l < LANES; l++) for (int mm = 0; mm <= F->JM; mm++) pt[l][mm] = bits[l][mm] ? qs[l][mm] : q0s[l][mm];
+  REAL loss = fast_fwd(F, &st, pt, &S);
+  if (grad) {
+    fast_bwd(F, &S, fast_free_wanted(F, bits), g);
+    for (int i = 0; i < m->nq; i++) grad[i] = R(0);
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm <= F->JM; mm++) if (bits[l][mm]) grad[F->adr[l][mm]] = g[l][mm];
+  }
+  return loss;
+}
+
+/* jaxopt ProjectedGradient in fast order (stacb_fast.cuh: solve); q0, params in the qpos layout */
+static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, const REAL *lb, const REAL *ub, const uint8_t *qmask,
+                             const REAL *kp, const REAL *kpmask, const REAL *site_pos, REAL tol, int maxiter, int maxls, REAL *params) {
+  const int NS = F->JM + 1;
+  fsites st; ffwd S;
+  fast_sites(F, site_pos, kp, kpmask, &st);
+  REAL q0s[LANES][FNS], x[LANES][FNS], y[LANES][FNS], g[LANES][FNS], xn[LANES][FNS], d[LANES][FNS], gt[LANES][FNS], pt[LANES][FNS];
+  REAL lbs[LANES][FNS], ubs[LANES][FNS];
+  int bits[LANES][FNS];
+  fast_gather(F, q0, q0s); fast_gather(F, lb, lbs); fast_gather(F, ub, ubs); fast_bits(F, qmask, bits);
+  const int fw = fast_free_wanted(F, bits);
+  /* passive coordinates: squared length of the move to clip(q0), dealt out over the lanes */
+  REAL sqp;
+  {
+    REAL part[LANES];
+    for (int l = 0; l < LANES; l++) {
+      REAL acc = R(0); int first = 1;
+      for (int i = l; i < F->npassive; i += LANES) {
+        int p = F->passive[i];
+        REAL dd = clipr(q0[p], lb[p], ub[p]) - q0[p];
+        acc = first ? dd * dd : r_fma(dd, dd, acc);
+        first = 0;
+      }
+      part[l] = acc;
+    }
+    sqp = butterfly32(part);
+  }
+  memcpy(params, q0, sizeof(REAL) * m->nq);
+  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) { x[l][mm] = F->valid[l][mm] ? q0s[l][mm] : R(0); y[l][mm] = x[l][mm]; }
+  REAL t = R(1), step = R(1), err = (REAL)INFINITY;
+  solve_info info = { err, 0, 0 };
+  if (maxiter <= 0) return info;
+  do {
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) pt[l][mm] = bits[l][mm] ? y[l][mm] : q0s[l][mm];
+    REAL fy = fast_fwd(F, &st, pt, &S);
+    fast_bwd(F, &S, fw, g);
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (!bits[l][mm]) g[l][mm] = R(0);
+    REAL stp = step;
+    int halv = 0;
+    for (;;) {
+      for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
+        xn[l][mm] = F->valid[l][mm] ? clipr(r_fma(-stp, g[l][mm], y[l][mm]), lbs[l][mm], ubs[l][mm]) : R(0);
+        d[l][mm] = xn[l][mm] - y[l][mm];
+      }
+      REAL sq = fast_dot(F, d, d), dg = fast_dot(F, d, g);
+      sq = sq + sqp;
+      for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) pt[l][mm] = bits[l][mm] ? xn[l][mm] : q0s[l][mm];
+      REAL fn = fast_fwd(F, &st, pt, &S);
+      info.ls_evals++;
+      REAL dec = stp * (fn - fy);
+      REAL cond = r_fma(stp, dg, R(0.5) * sq);
+      if (!(dec > cond + R_EPS) || halv >= maxls) break;
+      stp = stp * R(0.5); halv++;
+    }
+    /* S holds the state of the accepted candidate: gradient at x+ */
+    fast_bwd(F, &S, fw, gt);
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (!bits[l][mm]) gt[l][mm] = R(0);
+    step = (stp <= R(1e-6)) ? R(1) : stp / R(0.5);
+    REAL tn = R(0.5) * (R(1) + r_sqrt(r_fma(R(4) * t, t, R(1))));
+    REAL beta = (t - R(1)) / tn;
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
+      y[l][mm] = r_fma(beta, xn[l][mm] - x[l][mm], xn[l][mm]);
+      d[l][mm] = F->valid[l][mm] ? clipr(xn[l][mm] - gt[l][mm], lbs[l][mm], ubs[l][mm]) - xn[l][mm] : R(0);
+      x[l][mm] = xn[l][mm];
+    }
+    err = r_sqrt(fast_dot(F, d, d));
+    t = tn; info.iters++;
+    sqp = R(0);
+  } while (err > tol && info.iters < maxiter);
+  info.error = err;
+  for (int i = 0; i < F->npassive; i++) { int p = F->passive[i]; params[p] = clipr(q0[p], lb[p], ub[p]); }
+  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (F->valid[l][mm]) params[F->adr[l][mm]] = x[l][mm];
+  return info;
+}

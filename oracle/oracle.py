@@ -8,7 +8,9 @@ and DESIGN.md); the m-phase is pinned by the reference's own known-answer tests.
 ``Oracle(tree, site_bodies, dtype, mode)``
     dtype  np.float32 | np.float64
     mode   0 = MJX operation order (faithful restatement)
-           1 = canonical order (bit-matched to the CUDA kernels in float32)
+           1 = canonical order (bit-matched to the general CUDA kernels in float32)
+           2 = what libstacb computes by default: the register-resident solver's "fast order"
+               (oracle/fast_order.h) for the models it serves, mode 1 elsewhere
 """
 
 from __future__ import annotations
@@ -31,8 +33,8 @@ def _lib(dtype) -> C.CDLL:
     key = np.dtype(dtype).name
     if key not in _LIBS:
         p = HERE / "_build" / ("liboracle_f32.so" if key == "float32" else "liboracle_f64.so")
-        src = HERE / "stac_oracle.c"
-        if not p.exists() or p.stat().st_mtime < src.stat().st_mtime:
+        newest = max((HERE / n).stat().st_mtime for n in ("stac_oracle.c", "fast_order.h"))
+        if not p.exists() or p.stat().st_mtime < newest:
             build()
         _LIBS[key] = C.CDLL(str(p))
     return _LIBS[key]
@@ -90,6 +92,11 @@ class Oracle:
         )
         self.m = _OModel(tree.nbody, tree.nq, tree.njnt, self.K, *[_p(self._keep[k]) for k in list(self._keep)])
         self.real = C.c_float if self.dtype == np.float32 else C.c_double
+
+    @property
+    def fast_path(self) -> bool:
+        """True when mode 2 differs from mode 1 for this model (rodent, celegans: the register-resident solver)."""
+        return bool(self.lib.oracle_fast_path(C.byref(self.m)))
 
     def _f(self, a, shape=None):
         a = np.ascontiguousarray(a, dtype=self.dtype)

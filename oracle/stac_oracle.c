@@ -22,7 +22,7 @@
  *     (_m_opt); stac_mjx/compute_stac.py:17-104 (root_optimization), :170-278
  *     (pose_optimization); stac_mjx/utils.py:129-169 (make_qs / replace_qs).
  *
- * TWO ARITHMETIC ORDERS (argument `mode`)
+ * THREE ARITHMETIC ORDERS (argument `mode`)
  *   mode 0  "mjx order":  body-by-body world-frame FK exactly in the operation order
  *           of MJX smooth.kinematics, libm sin/cos, left-to-right sums, direct
  *           Jacobian-transpose gradient.  This is the faithful restatement.
@@ -33,6 +33,12 @@
  *           bit-identical to the GPU path, so solver decisions (line-search accepts,
  *           stopping iteration) coincide; tests/ quantify mode0-vs-mode1 and
  *           f32-vs-f64 spreads as the floating-point noise floor of the algorithm.
+ *
+ *   mode 2  "fast order": what libstacb computes by default.  For the models the register-resident
+ *           hinge-tree solver serves (rodent, C. elegans, ...) q_loss / _q_opt follow the operation
+ *           order of stacb_fast.cuh (fast_order.h); everything else is mode 1.
+ *   Mode 0 is FROZEN: tests/test_oracle_cpu.py pins a digest of its float64 outputs, so the
+ *   faithful restatement cannot drift when modes 1 / 2 follow a kernel change.
  *
  * Build: oracle/build.sh  (gcc -O2 -ffp-contract=off -mfma; REAL=float and REAL=double)
  */
@@ -631,6 +637,26 @@ static solve_info q_opt(const omodel *m, const osched *s, int mode, owork *w, co
   return info;
 }
 
+#include "fast_order.h"
+
+/* mode 2 = what libstacb computes by default: fast order where the register-resident solver serves the model, canonical
+ * order (mode 1) everywhere else (other models; FK outputs and m-phase statistics of every model) */
+static solve_info q_opt_any(const omodel *m, const osched *s, const ofast *F, int mode, owork *w, const REAL *q0, const REAL *lb, const REAL *ub,
+                            const uint8_t *qmask, const REAL *kp, const REAL *kpmask, const REAL *site_pos, REAL tol, int maxiter, int maxls,
+                            REAL *params) {
+  if (mode == 2 && F) return fast_q_opt(m, F, q0, lb, ub, qmask, kp, kpmask, site_pos, tol, maxiter, maxls, params);
+  return q_opt(m, s, mode, w, q0, lb, ub, qmask, kp, kpmask, site_pos, tol, maxiter, maxls, params);
+}
+
+/* 1 when mode 2 differs from mode 1 for this model (the register-resident solver serves it) */
+int oracle_fast_path(const omodel *m) {
+  osched *s = sched_create(m);
+  ofast *F = fast_create(m, s);
+  int r = F != NULL;
+  fast_destroy(F); sched_destroy(s);
+  return r;
+}
+
 /* ------------------------------------------------------------------ */
 /* exported entry points (ctypes)                                     */
 /* ------------------------------------------------------------------ */
@@ -653,7 +679,10 @@ int oracle_loss_grad(const omodel *m, int mode, const REAL *q, const REAL *q0, c
   osched *s = sched_create(m); owork *w = work_create(m);
   REAL *km = (REAL *)calloc(3 * m->nsite + 1, sizeof(REAL));
   for (int c = 0; c < 3 * m->nsite; c++) km[c] = kpmask[c] ? R(1) : R(0);
-  *loss = loss_eval(m, s, mode, w, q, q0, qmask, kp, km, site_pos, grad);
+  ofast *F = mode == 2 ? fast_create(m, s) : NULL;
+  if (F) *loss = fast_loss_eval(m, F, q, q0, qmask, kp, km, site_pos, grad);
+  else *loss = loss_eval(m, s, mode, w, q, q0, qmask, kp, km, site_pos, grad);
+  fast_destroy(F);
   free(km); work_destroy(w); sched_destroy(s);
   return 0;
 }
@@ -664,8 +693,10 @@ int oracle_q_opt(const omodel *m, int mode, const REAL *q0, const REAL *lb, cons
   osched *s = sched_create(m); owork *w = work_create(m);
   REAL *km = (REAL *)calloc(3 * m->nsite + 1, sizeof(REAL));
   for (int c = 0; c < 3 * m->nsite; c++) km[c] = kpmask[c] ? R(1) : R(0);
-  solve_info si = q_opt(m, s, mode, w, q0, lb, ub, qmask, kp, km, site_pos, tol, maxiter, maxls, params);
+  ofast *F = mode == 2 ? fast_create(m, s) : NULL;
+  solve_info si = q_opt_any(m, s, F, mode, w, q0, lb, ub, qmask, kp, km, site_pos, tol, maxiter, maxls, params);
   *error = si.error; *iters = si.iters; *ls_evals = si.ls_evals;
+  fast_destroy(F);
   free(km); work_destroy(w); sched_destroy(s);
   return 0;
 }
@@ -691,6 +722,7 @@ int oracle_pose_clip(const omodel *m, int mode, const REAL *kp, int F, REAL *qpo
                      int32_t *root_stats) {
   int nq = m->nq, K = m->nsite, nb = m->nbody;
   osched *s = sched_create(m); owork *w = work_create(m);
+  ofast *Fz = mode == 2 ? fast_create(m, s) : NULL;
   REAL *ones = (REAL *)calloc(3 * K + 1, sizeof(REAL)), *trunk = (REAL *)calloc(3 * K + 1, sizeof(REAL));
   uint8_t *allq = (uint8_t *)calloc(nq + 1, 1), *rootq = (uint8_t *)calloc(nq + 1, 1);
   REAL *q0 = (REAL *)calloc(nq, sizeof(REAL)), *par = (REAL *)calloc(nq, sizeof(REAL)), *qm = (REAL *)calloc(nq, sizeof(REAL));
@@ -701,7 +733,7 @@ int oracle_pose_clip(const omodel *m, int mode, const REAL *kp, int F, REAL *qpo
     for (int rep = 0; rep < 2; rep++) {
       memcpy(q0, qpos, sizeof(REAL) * nq);
       for (int c = 0; c < 3; c++) q0[c] = kp[3 * root_kp_idx + c];
-      solve_info si = q_opt(m, s, mode, w, q0, lb, ub, rootq, kp, trunk, site_pos, tol, maxiter, maxls, par);
+      solve_info si = q_opt_any(m, s, Fz, mode, w, q0, lb, ub, rootq, kp, trunk, site_pos, tol, maxiter, maxls, par);
       make_qs(nq, q0, rootq, par, qm);
       replace_qs(m, s, mode, w, qm, qpos);
       if (root_stats) { root_stats[2 * rep] = si.iters; root_stats[2 * rep + 1] = si.ls_evals; }
@@ -711,13 +743,13 @@ int oracle_pose_clip(const omodel *m, int mode, const REAL *kp, int F, REAL *qpo
     const REAL *kpf = kp + (size_t)f * 3 * K;
     solve_info si;
     memcpy(q0, qpos, sizeof(REAL) * nq);
-    si = q_opt(m, s, mode, w, q0, lb, ub, allq, kpf, ones, site_pos, tol, maxiter, maxls, par);
+    si = q_opt_any(m, s, Fz, mode, w, q0, lb, ub, allq, kpf, ones, site_pos, tol, maxiter, maxls, par);
     replace_qs(m, s, mode, w, par, qpos);
     if (iters_out) { iters_out[(size_t)f * (1 + P)] = si.iters; ls_out[(size_t)f * (1 + P)] = si.ls_evals; }
     for (int p = 0; p < P; p++) {
       const uint8_t *pm = part_masks + (size_t)p * nq;
       memcpy(q0, qpos, sizeof(REAL) * nq);
-      si = q_opt(m, s, mode, w, q0, lb, ub, pm, kpf, ones, site_pos, tol, maxiter, maxls, par);
+      si = q_opt_any(m, s, Fz, mode, w, q0, lb, ub, pm, kpf, ones, site_pos, tol, maxiter, maxls, par);
       make_qs(nq, q0, pm, par, qm);
       replace_qs(m, s, mode, w, qm, qpos);
       if (iters_out) { iters_out[(size_t)f * (1 + P) + 1 + p] = si.iters; ls_out[(size_t)f * (1 + P) + 1 + p] = si.ls_evals; }
@@ -731,6 +763,7 @@ int oracle_pose_clip(const omodel *m, int mode, const REAL *kp, int F, REAL *qpo
     if (err_out) err_out[f] = si.error;
   }
   free(ones); free(trunk); free(allq); free(rootq); free(q0); free(par); free(qm);
+  fast_destroy(Fz);
   work_destroy(w); sched_destroy(s);
   return 0;
 }

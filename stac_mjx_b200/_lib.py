@@ -18,7 +18,9 @@ SYMBOLS = (
     "stacb_pose_clips",
     "stacb_m_stats",
     "stacb_fma_peak",
-    "stacb_set_mode",
+    "stacb_tree_set_mode",
+    "stacb_tree_set_path",
+    "stacb_tree_path",
     "stacb_last_error",
     "stacb_version",
 )
@@ -76,7 +78,9 @@ def lib() -> C.CDLL:
         )
         L.stacb_m_stats.argtypes = [vp] * 6 + [i32, vp]
         L.stacb_fma_peak.argtypes = [vp, i32, i32, i32, vp]
-        L.stacb_set_mode.argtypes = [i32]
+        L.stacb_tree_set_mode.argtypes = [vp, i32]
+        L.stacb_tree_set_path.argtypes = [vp, i32]
+        L.stacb_tree_path.argtypes = [vp]
         L.stacb_last_error.restype = C.c_char_p
         L.stacb_version.restype = i32
         _lib = L

@@ -14,11 +14,17 @@ for v in $VARIANTS; do
   $NVCC $FLAGS -DV_CPL=$1 -DV_NB=$2 -DV_NBF=$3 -DV_SPL=$4 -DV_JM=$5 -c stacb_variant.cu -o _obj/variant_$v.o > _obj/variant_$v.log 2>&1 &
   pids="$pids $!"
 done
+FAST=$(sed -n 's/^#define STACB_FAST_VARIANTS(X)//p' stacb_variants.h | sed 's/X(\([0-9]*\), *\([0-9]*\), *\([0-9]*\))/\1_\2_\3/g')
+for v in $FAST; do
+  set -- $(echo $v | tr '_' ' ')
+  $NVCC $FLAGS -Xptxas -v -DV_FJM=$1 -DV_FRT=$2 -DV_FNBF=$3 -c stacb_fast_variant.cu -o _obj/fast_$v.o > _obj/fast_$v.log 2>&1 &
+  pids="$pids $!"
+done
 $NVCC $FLAGS -c stacb_abi.cu -o _obj/abi.o > _obj/abi.log 2>&1 &
 pids="$pids $!"
 rc=0
 for p in $pids; do wait $p || rc=1; done
-cat _obj/*.log
+cat _obj/*.log | grep -v -e '^ptxas info    : Function properties' -e 'bytes stack frame' -e '^ptxas info    : Compiling' -e '^ptxas info    : 0 bytes gmem' || true
 [ $rc -eq 0 ] || { echo "stacb build failed"; exit 1; }
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libstacb.so _obj/*.o
 echo "built $(cd .. && pwd)/libstacb.so"

@@ -55,10 +55,24 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(STACB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// RAII: entry points run on the handle's device and leave the caller's current device as they found it
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct stacb_tree {
   int device;
   DevTree T;
   int cpl, bpl_act, bpl_full, jm_act;
+  bool fast_ok = false;                  // the register-resident hinge-tree solver applies (stacb_fast.cuh)
+  std::atomic<int> mode{-1};             // scheduling override of stacb_pose_clips (stacb_tree_set_mode)
+  std::atomic<int> path{0};              // 0 = register-resident solver where it applies, 1 = general kernels only
   std::vector<void *> allocs;
   int *counter;                          // pool of work counters: one per in-flight launch (launches may overlap on different streams)
   mutable std::atomic<unsigned> next{0};
@@ -132,8 +146,12 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   if (!d || !out) return fail(STACB_E_INVALID, "null argument");
   const stacb_tree_desc &m = *d;
   if (m.nbody < 2 || m.nq < 1 || m.njnt < 0 || m.nsite < 1) return fail(STACB_E_INVALID, "empty model");
+  std::vector<int> path_stack{0};  // depth-first pre-order <=> every body's parent is on the current root-to-node path
   for (int b = 1; b < m.nbody; b++) {
     if (m.body_parent[b] < 0 || m.body_parent[b] >= b) return fail(STACB_E_INVALID, "body ids must be in depth-first pre-order");
+    while (!path_stack.empty() && path_stack.back() != m.body_parent[b]) path_stack.pop_back();
+    if (path_stack.empty()) return fail(STACB_E_INVALID, "body ids must be in depth-first pre-order (subtrees must be contiguous id ranges)");
+    path_stack.push_back(b);
     if (m.body_jntnum[b] > JMAX) return fail(STACB_E_UNSUPPORTED, "more than 3 joints on one body");
     for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
       const int j = m.body_jntadr[b] + jj, t = m.jnt_type[j];
@@ -145,7 +163,8 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   }
   for (int k = 0; k < m.nsite; k++)
     if (m.site_body[k] <= 0 || m.site_body[k] >= m.nbody) return fail(STACB_E_INVALID, "keypoint site must be attached to a non-world body");
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CUDA_TRY(guard.err);
   stacb_tree *t = new stacb_tree();
   t->device = device;
   const int nb = m.nbody, K = m.nsite;
@@ -205,6 +224,30 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   for (size_t e = 0; e < act.size(); e++) t->jm_act = std::max(t->jm_act, rec_a[e * REC + R_NJNT]);
   t->cpl = (m.nq + 31) / 32; t->bpl_act = (T.act.n + 31) / 32; t->bpl_full = (T.full.n + 31) / 32;
   T.nqp = 32 * t->cpl; T.pqn = std::max(T.act.n, T.full.n); T.npre = 32 * T.spl;
+  // Register-resident solver: active subtree of at most 31 bodies with hinges only plus (optionally) the primary free joint,
+  // at most 31 sites, no quaternion joint anywhere else.  Its solver slots cover the active hinges and the free joint; every
+  // other qpos address is "passive" (zero gradient).
+  {
+    std::vector<char> covered(m.nq, 0);
+    for (size_t e = 0; e < act.size(); e++) {
+      const int *r = rec_a.data() + e * REC;
+      for (int jj = 0; jj < r[R_NJNT]; jj++) {
+        const int *jr = r + R_JNT + J_STRIDE * jj;
+        if (jr[J_TYPE] == STACB_JNT_HINGE) covered[jr[J_ADR]] = 1;
+      }
+    }
+    if (T.free_e >= 0)
+      for (int i = 0; i < 7; i++) covered[T.free_adr + i] = 1;
+    std::vector<int> passive;
+    for (int i = 0; i < m.nq; i++)
+      if (!covered[i]) passive.push_back(i);
+    T.npassive = (int)passive.size();
+    if ((rc = upload(t, passive, &T.passive))) {
+      stacb_tree_destroy(t);
+      return rc;
+    }
+    t->fast_ok = T.act.n <= 31 && K <= 31 && !T.any_other && T.nquat == (T.free_e >= 0 ? 1 : 0) && (passive.empty() || passive[0] >= 3);
+  }
   void *cnt = nullptr;
   if (cudaMalloc(&cnt, kCounterPool * sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
   t->allocs.push_back(cnt);
@@ -227,20 +270,45 @@ namespace stacb {
   cudaError_t launch_batch_##c##_##n##_##f##_##p##_##j(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t);
 STACB_VARIANTS(X)
 #undef X
+#define X(j, r, f)                                                                                                   \
+  cudaError_t launch_fast_pose_##j##_##r##_##f(const DevTree &, const PoseArgs &, int, int, size_t, int, cudaStream_t); \
+  cudaError_t launch_fast_batch_##j##_##r##_##f(const DevTree &, const BatchArgs &, int, int, cudaStream_t);
+STACB_FAST_VARIANTS(X)
+#undef X
 }  // namespace stacb
+
+static bool fits_fast(const stacb_tree *t, int jm, int rt, int nbf) {
+  return t->fast_ok && t->path.load() == 0 && t->jm_act <= jm && t->T.act.rounds <= rt && t->bpl_full <= nbf;
+}
 
 static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl, int jm) {
   return t->cpl <= cpl && t->bpl_act <= nb && t->bpl_full <= nbf && t->T.spl <= spl && t->jm_act <= jm;
 }
 
-static int g_force_mode = -1;  // -1 auto, 0 throughput, 1 latency (four warps per chain), 2 dense throughput, 3 grouped latency
-
 static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
-  CUDA_TRY(cudaSetDevice(t->device));
-  a.counter = t->counter + (t->next.fetch_add(1) % kCounterPool);  // the handle stays logically immutable: each launch owns a counter
+  DeviceGuard guard(t->device);
+  CUDA_TRY(guard.err);
+  // each launch owns a work counter; the pool bounds the number of launches of one handle that may be in flight at once
+  a.counter = t->counter + (t->next.fetch_add(1) % kCounterPool);
   CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  const int g_force_mode = t->mode.load();
+  {
+    // register-resident solver: latency mode (2 * NC warps per chain) for few chains, throughput mode (one warp per chain)
+    // for many, dense throughput mode (registers capped for 16 warps per SM) from 16 chains per SM
+    int sched = (a.C <= 2 * sms) ? 1 : (a.C >= 16 * sms ? 2 : 0);
+    if (g_force_mode >= 0) sched = g_force_mode;
+    const int nc = sched == 1 ? 2 : (sched == 3 ? 3 : 0);
+    const size_t area = ((size_t)2 * t->T.nqp + 7 * (size_t)t->T.pqn) * 4;
+    const int block = nc ? 64 * nc : 128;
+    const size_t smem = nc ? area + 8192 : 4 * area;  // latency mode: + the exchange area of solve_coop (< 8 KB for 4 slots, NC <= 3)
+    const int grid = nc ? std::min(a.C, sms * 8) : std::min((a.C + 3) / 4, sms * 16);
+#define X(j, r, f) \
+  if (fits_fast(t, j, r, f)) { CUDA_TRY(launch_fast_pose_##j##_##r##_##f(t->T, a, grid, block, smem, sched, s)); return STACB_OK; }
+    STACB_FAST_VARIANTS(X)
+#undef X
+  }
   // Few chains: latency mode, one CTA of four cooperating warps per chain (speculative line search, see solve4).
   // Many chains: throughput mode, one warp per chain, four chains per CTA.
   const size_t chain_bytes = (size_t)chain_smem_floats(t->T) * 4;
@@ -264,12 +332,19 @@ static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
 }
 
 static int run_batch(const stacb_tree *t, const BatchArgs &a, cudaStream_t s) {
-  CUDA_TRY(cudaSetDevice(t->device));
+  DeviceGuard guard(t->device);
+  CUDA_TRY(guard.err);
   if (a.B <= 0) return STACB_OK;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
   const int wpb = (a.B <= 2 * sms) ? 1 : 4;
   const int grid = std::min((a.B + wpb - 1) / wpb, sms * 16);
+  if (a.mode == 1 || a.mode == 2) {  // q_loss / _q_opt share the arithmetic of the pose kernel that serves this model
+#define X(j, r, f) \
+  if (fits_fast(t, j, r, f)) { CUDA_TRY(launch_fast_batch_##j##_##r##_##f(t->T, a, grid, 32 * wpb, s)); return STACB_OK; }
+    STACB_FAST_VARIANTS(X)
+#undef X
+  }
   const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
   if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
 #define X(c, n, f, p, j) \
@@ -343,10 +418,26 @@ extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, vo
   return STACB_OK;
 }
 
-extern "C" int stacb_set_mode(int mode) {
-  if (mode < -1 || mode > 3) return fail(STACB_E_INVALID, "stacb_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency), 2 (dense throughput) or 3 (grouped latency)");
-  g_force_mode = mode;
+extern "C" int stacb_tree_set_mode(stacb_tree *t, int mode) {
+  if (!t || mode < -1 || mode > 3)
+    return fail(STACB_E_INVALID, "stacb_tree_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency), 2 (dense throughput) or 3 (wide latency)");
+  t->mode.store(mode);
   return STACB_OK;
+}
+
+extern "C" int stacb_tree_set_path(stacb_tree *t, int path) {
+  if (!t || path < 0 || path > 1) return fail(STACB_E_INVALID, "stacb_tree_set_path: path must be 0 (auto) or 1 (general kernels only)");
+  t->path.store(path);
+  return STACB_OK;
+}
+
+extern "C" int stacb_tree_path(const stacb_tree *t) {
+  if (!t) return -1;
+#define X(j, r, f) \
+  if (fits_fast(t, j, r, f)) return 1;
+  STACB_FAST_VARIANTS(X)
+#undef X
+  return 0;
 }
 
 extern "C" const char *stacb_last_error(void) { return g_err.c_str(); }

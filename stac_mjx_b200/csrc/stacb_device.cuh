@@ -45,6 +45,8 @@ struct DevTree {
   int free_e, free_adr, free_sa, free_se;  // primary free joint: active-set element (-1 if none), qpos address, site range
   int any_other;          // some active joint is neither a hinge nor the primary free joint (ball / slide / extra free)
   const int *quat_adr;    // [nquat] qpos address of each quaternion
+  int npassive;           // register-resident path (stacb_fast.cuh): qpos addresses outside its solver slots
+  const int *passive;     // [npassive] ascending
 };
 
 __host__ __device__ inline int role_smem_floats(const DevTree &T) { return 2 * T.nqp + 7 * T.pqn; }  // qbuf, gbuf, PQ
@@ -973,7 +975,8 @@ struct PoseArgs {
 // MODE 3: grouped latency for wide trees: the 4 roles of latency mode, each carried out by GRP = 3 member warps that
 //         deal the bodies of the tree out among themselves (NB is then the number of bodies per lane of ONE member).
 constexpr int GRP = 3;
-template <int CPL, int NB, int NBF, int SPL, int MODE>
+// JMV = JM of the translation unit: part of the kernel's symbol, so variants that differ only in joint slots cannot clash at link time
+template <int CPL, int NB, int NBF, int SPL, int MODE, int JMV = JM>
 __global__ void __launch_bounds__(MODE == 3 ? 128 * GRP : 128, MODE == 2 ? 4 : 1) pose_clips_kernel(DevTree T, PoseArgs a) {
   constexpr bool COOP = MODE == 1 || MODE == 3;
   constexpr int G = MODE == 3 ? GRP : 1;
@@ -1092,7 +1095,7 @@ struct BatchArgs {
   float *out_a, *out_b, *out_c, *out_d; int32_t *iters, *ls_evals; int B; int mode;  // 0 fk, 1 loss_grad, 2 q_opt, 3 m_stats
 };
 
-template <int CPL, int NB, int NBF, int SPL>
+template <int CPL, int NB, int NBF, int SPL, int JMV = JM>
 __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

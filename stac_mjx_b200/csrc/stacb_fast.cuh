@@ -58,6 +58,7 @@ struct LaneC {
 struct SiteC {
   int k;       // keypoint index of the site at sorted position `lane`, -1 if none
   int eb;      // lane of the site's body
+  int ef;      // full-set element of the site's body (per-frame outputs)
   V3 off, kp, km;
 };
 
@@ -116,11 +117,12 @@ __device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, in
 }
 
 __device__ __forceinline__ void site_init(SiteC &st, const DevTree &T, int lane, const float *__restrict__ site_pos) {
-  st.k = -1; st.eb = IDL;
+  st.k = -1; st.eb = IDL; st.ef = 0;
   st.off = mk3(0.f, 0.f, 0.f); st.kp = mk3(0.f, 0.f, 0.f); st.km = mk3(0.f, 0.f, 0.f);
   if (lane < T.K) {
     st.k = __ldg(T.site_order + lane);
     st.eb = __ldg(T.site_eact + lane);
+    st.ef = __ldg(T.site_efull + lane);
     if (site_pos) st.off = mk3(__ldg(site_pos + 3 * st.k), __ldg(site_pos + 3 * st.k + 1), __ldg(site_pos + 3 * st.k + 2));
   }
 }
@@ -366,8 +368,7 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
 template <int NS, int NC>
 struct Xchg {  // shared memory
   float g[2][NC][32 * NS];
-  float acc[2][NC], err[2][NC], fy[2][NC];
-  float bad;
+  float acc[2][NC], err[2][NC], fy[2][NC], nf[2][NC];  // accepted flag, error at x+_j, f(y'_j), non-finite f(x+_j)
 };
 
 template <int JM, int RT, int NC>
@@ -427,7 +428,7 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
       if (u.lane == 0) {
         xc->acc[par][j] = rejected ? 0.f : 1.f;
         xc->err[par][j] = err;
-        if (!(f - f == 0.0f)) xc->bad = 1.f;
+        xc->nf[par][j] = (f - f == 0.0f) ? 0.f : 1.f;
       }
     } else {
 #pragma unroll
@@ -440,6 +441,9 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     for (int i = NC - 1; i >= 0; i--) k = (xc->acc[par][i] != 0.f) ? i : k;
     const int rp = par;
     par ^= 1;
+#pragma unroll
+    for (int i = 0; i < NC; i++)  // non-finite losses among the candidates the sequential line search evaluates
+      if ((k < 0 || i <= k) && xc->nf[rp][i] != 0.f) out.bad = true;
     if (k < 0) {  // every candidate rejected: next NC step sizes
       base += NC;
 #pragma unroll
@@ -470,6 +474,286 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     base = 0;
   }
   return out;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// solver slots <-> qpos addresses
+// ------------------------------------------------------------------------------------------
+template <int JM>
+struct SlotAdr { int adr[JM + 1]; };
+
+template <int JM, int RT>
+__device__ __forceinline__ void slots_init(Slots<JM + 1> &co, SlotAdr<JM> &sa, const LaneC<JM, RT> &L, const DevTree &T, int lane,
+                                           const float *__restrict__ lb, const float *__restrict__ ub) {
+#pragma unroll
+  for (int j = 0; j < JM; j++) { co.valid[j] = L.hinge[j]; sa.adr[j] = L.adr[j]; }
+  co.valid[JM] = T.free_e >= 0 && lane < 7;
+  sa.adr[JM] = co.valid[JM] ? T.free_adr + lane : 0;
+#pragma unroll
+  for (int m = 0; m <= JM; m++) {
+    co.lb[m] = (co.valid[m] && lb) ? lb[sa.adr[m]] : 0.f;
+    co.ub[m] = (co.valid[m] && ub) ? ub[sa.adr[m]] : 0.f;
+  }
+}
+
+// which qpos addresses a solve optimises: an explicit u8 mask, or every address below `lim`
+struct MaskSpec { const uint8_t *m; int lim; };
+__device__ __forceinline__ bool mask_has(const MaskSpec &ms, int adr) { return ms.m ? ms.m[adr] != 0 : adr < ms.lim; }
+
+template <int JM>
+__device__ __forceinline__ unsigned slot_bits(const Slots<JM + 1> &co, const SlotAdr<JM> &sa, const MaskSpec &ms) {
+  unsigned b = 0;
+#pragma unroll
+  for (int m = 0; m <= JM; m++)
+    if (co.valid[m] && mask_has(ms, sa.adr[m])) b |= 1u << m;
+  return b;
+}
+
+template <int JM>
+__device__ __forceinline__ void slots_gather(const Slots<JM + 1> &co, const SlotAdr<JM> &sa, const float *src, float (&q)[JM + 1]) {
+#pragma unroll
+  for (int m = 0; m <= JM; m++) q[m] = co.valid[m] ? src[sa.adr[m]] : 0.f;
+}
+template <int JM>
+__device__ __forceinline__ void slots_scatter(const Slots<JM + 1> &co, const SlotAdr<JM> &sa, const float (&q)[JM + 1], float *dst) {
+#pragma unroll
+  for (int m = 0; m <= JM; m++)
+    if (co.valid[m]) dst[sa.adr[m]] = q[m];
+}
+
+// Passive coordinates (hinges outside the active subtree): zero gradient, so a solve moves them to clip(q0) in its first
+// iteration and never again.  Squared length of that move (enters the first line search), lanes deal the list out.
+__device__ __forceinline__ float passive_sq(const DevTree &T, int lane, const float *q, const float *__restrict__ lb, const float *__restrict__ ub) {
+  float acc = 0.f;
+  bool first = true;
+  for (int i = lane; i < T.npassive; i += 32) {
+    const int p = __ldg(T.passive + i);
+    const float v = q[p];
+    const float d = clipf(v, lb[p], ub[p]) - v;
+    acc = first ? d * d : fmaf(d, d, acc);
+    first = false;
+  }
+  return warp_sum(acc);
+}
+
+// replace_qs as far as the free joint's quaternion is concerned (MJX kinematics normalises it in qpos), in the slot layout
+template <int JM>
+__device__ __forceinline__ void normalize_free(const Uni &u, float (&q)[JM + 1]) {
+  if (!u.has_free) return;
+  float fr[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) fr[i] = __shfl_sync(FULL, q[JM], 3 + i);
+  float d;
+  const Q4 qn = normalize4(mk4(fr[0], fr[1], fr[2], fr[3]), &d);
+  float v = q[JM];
+  v = u.lane == 3 ? qn.w : v; v = u.lane == 4 ? qn.x : v; v = u.lane == 5 ? qn.y : v; v = u.lane == 6 ? qn.z : v;
+  q[JM] = v;
+}
+
+// Full-model FK of the qpos vector in ch.qbuf (normalised in place) and the per-frame outputs: the general cold path.
+template <int NBF>
+__device__ __forceinline__ void outputs_from_qbuf(const Chain &ch, const SiteC &st, float *qpos_o, float *xpos_o, float *xquat_o, float *sites_o) {
+  V3 P[NBF];
+  Q4 Q[NBF];
+  fk_cold<NBF>(ch, ch.T.full, P, Q);
+  if (qpos_o)
+    for (int i = ch.lane; i < ch.T.nq; i += 32) qpos_o[i] = ch.qbuf[i];
+  const DevSet &S = ch.T.full;
+#pragma unroll
+  for (int i = 0; i < NBF; i++) {
+    const int e = ch.lane + 32 * i;
+    if (e < S.n) {
+      const int b = __ldg(S.rec + (size_t)e * REC + R_BODY);
+      if (xpos_o) { xpos_o[3 * b] = P[i].x; xpos_o[3 * b + 1] = P[i].y; xpos_o[3 * b + 2] = P[i].z; }
+      if (xquat_o) { xquat_o[4 * b] = Q[i].w; xquat_o[4 * b + 1] = Q[i].x; xquat_o[4 * b + 2] = Q[i].y; xquat_o[4 * b + 3] = Q[i].z; }
+    }
+  }
+  if (ch.lane == 0) {
+    if (xpos_o) { xpos_o[0] = 0.f; xpos_o[1] = 0.f; xpos_o[2] = 0.f; }
+    if (xquat_o) { xquat_o[0] = 1.f; xquat_o[1] = 0.f; xquat_o[2] = 0.f; xquat_o[3] = 0.f; }
+  }
+  if (sites_o && st.k >= 0) {
+    const float *o = ch.PQ + 7 * st.ef;
+    const V3 s = add3(lds3(o), rotate(st.off, lds4(o + 3)));
+    sites_o[3 * st.k] = s.x; sites_o[3 * st.k + 1] = s.y; sites_o[3 * st.k + 2] = s.z;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+// NC == 0: throughput mode, one warp per chain, four chains per CTA (MINB CTAs per SM requested from the compiler);
+// NC >= 2: latency mode, 2 * NC warps cooperate on one chain (solve_coop).
+template <int JM, int RT, int NBF, int NC, int MINB>
+__global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(DevTree T, PoseArgs a) {
+  constexpr bool COOP = NC > 0;
+  constexpr int NS = JM + 1;
+  extern __shared__ float smem[];
+  __shared__ int s_chain;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int area = 2 * T.nqp + 7 * T.pqn;  // qbuf [nqp], (unused) [nqp], PQ [7 pqn]
+  Chain ch(T, smem + (size_t)(COOP ? 0 : wib) * area, nullptr, lane, 0, 1, 0);
+  Xchg<NS, (NC > 0 ? NC : 1)> *xc = reinterpret_cast<Xchg<NS, (NC > 0 ? NC : 1)> *>(smem + area);
+  const bool writer = !COOP || wib == 0;
+  LaneC<JM, RT> L;
+  lane_init<JM, RT>(L, T, lane);
+  SiteC st;
+  site_init(st, T, lane, a.site_pos);
+  Slots<NS> co;
+  SlotAdr<JM> sa;
+  slots_init<JM, RT>(co, sa, L, T, lane, a.lb, a.ub);
+  Uni u;
+  u.lane = lane; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.free_e >= 0;
+  u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls;
+  const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P, npassive = T.npassive;
+  const MaskSpec full_ms = {nullptr, nq}, root_ms = {nullptr, a.root_dims};
+  const unsigned full_bits = slot_bits<JM>(co, sa, full_ms), root_bits = slot_bits<JM>(co, sa, root_ms);
+  const int n_root = a.do_root ? 2 : 0;           // two root solves on frame 0 (compute_stac.py:64-98)
+  const int n_pose = (a.do_root == 2) ? 0 : a.F;  // do_root == 2: root optimisation only
+  const int n_stage = n_root + n_pose * S1;
+  int par = 0;
+
+  for (;;) {
+    int c = 0;
+    if (COOP) {
+      if (threadIdx.x == 0) s_chain = atomicAdd(a.counter, 1);
+      __syncthreads();
+      c = s_chain;
+    } else {
+      if (lane == 0) c = atomicAdd(a.counter, 1);
+      c = __shfl_sync(FULL, c, 0);
+    }
+    if (c >= a.C) break;
+    if (writer)
+      for (int i = lane; i < nq; i += 32) ch.qbuf[i] = a.qpos_io[(size_t)c * nq + i];
+    if (COOP) __syncthreads(); else __syncwarp();
+    float q[NS], q0[NS], x[NS];
+    slots_gather<JM>(co, sa, ch.qbuf, q);
+    bool bad = false;
+    const float *kpc = a.kp + (size_t)c * a.F * 3 * K;
+    for (int sidx = 0; sidx < n_stage; sidx++) {
+      const bool is_root = sidx < n_root;
+      const int f = is_root ? 0 : (sidx - n_root) / S1;   // frame
+      const int sg = is_root ? 0 : (sidx - n_root) % S1;  // 0: whole body, 1..P: INDIVIDUAL_PART_OPTIMIZATION masks
+      unsigned bits;
+      MaskSpec ms;
+      if (is_root) {
+        if (sidx == 0) { site_load_kp(st, kpc); site_mask_kp(st, a.trunk_kps); }
+        bits = root_bits;
+        ms = root_ms;
+      } else {
+        if (sg == 0) { site_load_kp(st, kpc + (size_t)f * 3 * K); if (f == 0) site_mask_kp(st, nullptr); }
+        ms.m = (sg == 0) ? nullptr : a.part_masks + (size_t)(sg - 1) * nq;
+        ms.lim = nq;
+        bits = (sg == 0) ? full_bits : slot_bits<JM>(co, sa, ms);
+      }
+#pragma unroll
+      for (int m = 0; m < NS; m++) {
+        q0[m] = q[m];
+        if (is_root && co.valid[m] && sa.adr[m] < 3) q0[m] = kpc[3 * a.root_kp_idx + sa.adr[m]];  // re-seed the root translation
+      }
+      const float sqp = npassive ? passive_sq(T, lane, ch.qbuf, a.lb, a.ub) : 0.f;
+      SolveOut so;
+      if constexpr (COOP) so = solve_coop<JM, RT, NC>(L, st, u, co, q0, bits, sqp, x, xc, wib, par);
+      else so = solve<JM, RT>(L, st, u, co, q0, bits, sqp, x);
+#pragma unroll
+      for (int m = 0; m < NS; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];  // utils.make_qs
+      bad |= so.bad;
+      if (npassive && u.maxiter > 0) {  // the passive coordinates the solve covers end at clip(q0)
+        if (writer)
+          for (int i = lane; i < npassive; i += 32) {
+            const int p = __ldg(T.passive + i);
+            if (mask_has(ms, p)) ch.qbuf[p] = clipf(ch.qbuf[p], a.lb[p], a.ub[p]);
+          }
+        if (COOP) __syncthreads(); else __syncwarp();
+      }
+      if (is_root) {
+        if (a.root_stats && lane == 0 && writer) { a.root_stats[4 * c + 2 * sidx] = so.iters; a.root_stats[4 * c + 2 * sidx + 1] = so.ls; }
+      } else {
+        const size_t fi = (size_t)c * a.F + f;
+        if (a.iters && lane == 0 && writer) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
+        if (sg == a.P && writer) {  // last solve of the frame: full-model FK of the raw solution -> outputs
+          slots_scatter<JM>(co, sa, q, ch.qbuf);
+          __syncwarp();
+          outputs_from_qbuf<NBF>(ch, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
+                                 a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
+          if (a.err && lane == 0) a.err[fi] = so.err;
+        }
+      }
+      normalize_free<JM>(u, q);  // replace_qs: kinematics normalises the quaternion (same arithmetic as the cold FK above)
+    }
+    if (writer) {
+      slots_scatter<JM>(co, sa, q, ch.qbuf);
+      __syncwarp();
+      for (int i = lane; i < nq; i += 32) a.qpos_io[(size_t)c * nq + i] = ch.qbuf[i];
+      if (a.status && lane == 0) a.status[c] = bad ? 1 : 0;
+    }
+    if (COOP) __syncthreads(); else __syncwarp();
+  }
+}
+
+// B independent items: q_loss + gradient (mode 1) or one FISTA solve (mode 2); one warp per item.
+template <int JM, int RT>
+__global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a) {
+  constexpr int NS = JM + 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  LaneC<JM, RT> L;
+  lane_init<JM, RT>(L, T, lane);
+  SiteC st;
+  site_init(st, T, lane, a.site_pos);
+  site_mask_u8(st, a.kp_mask);
+  Slots<NS> co;
+  SlotAdr<JM> sa;
+  slots_init<JM, RT>(co, sa, L, T, lane, a.lb, a.ub);
+  Uni u;
+  u.lane = lane; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.free_e >= 0;
+  u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls;
+  const int nq = T.nq, K = T.K;
+  const MaskSpec ms = {a.q_mask, nq};
+  const unsigned bits = slot_bits<JM>(co, sa, ms);
+  for (int b = blockIdx.x * wpb + wib; b < a.B; b += gridDim.x * wpb) {
+    float q[NS], q0[NS];
+    const float *qb = a.q + (size_t)b * nq;
+    slots_gather<JM>(co, sa, qb, q);
+    if (a.q0) slots_gather<JM>(co, sa, a.q0 + (size_t)b * nq, q0);
+    else {
+#pragma unroll
+      for (int m = 0; m < NS; m++) q0[m] = q[m];
+    }
+    site_load_kp(st, a.kp + (size_t)b * 3 * K);
+    if (a.mode == 1) {
+      float pt[NS], g[NS];
+#pragma unroll
+      for (int m = 0; m < NS; m++) pt[m] = ((bits >> m) & 1u) ? q[m] : q0[m];
+      Fwd<JM> S;
+      const float loss = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+      if (lane == 0) a.out_a[b] = loss;
+      if (a.out_b) {
+        eval_bwd<JM, RT>(L, S, lane, free_wanted_of<JM>(u, bits), u.free_sa, u.free_se, g);
+        float *go = a.out_b + (size_t)b * nq;
+        for (int i = lane; i < nq; i += 32) go[i] = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < NS; m++)
+          if (co.valid[m] && ((bits >> m) & 1u)) go[sa.adr[m]] = g[m];
+      }
+    } else {
+      float x[NS];
+      const float sqp = T.npassive ? passive_sq(T, lane, qb, a.lb, a.ub) : 0.f;
+      const SolveOut so = solve<JM, RT>(L, st, u, co, q, bits, sqp, x);
+      float *po = a.out_a + (size_t)b * nq;
+      for (int i = lane; i < T.npassive; i += 32) {
+        const int p = __ldg(T.passive + i);
+        po[p] = u.maxiter > 0 ? clipf(qb[p], a.lb[p], a.ub[p]) : qb[p];
+      }
+      slots_scatter<JM>(co, sa, x, po);
+      if (lane == 0) { a.out_b[b] = so.err; a.iters[b] = so.iters; a.ls_evals[b] = so.ls; }
+    }
+    __syncwarp();
+  }
 }
 
 }  // namespace fast

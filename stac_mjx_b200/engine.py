@@ -72,8 +72,17 @@ class Engine:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     def set_mode(self, mode: int) -> None:
-        """Scheduling of pose_clips: -1 auto, 0 throughput (warp per chain), 1 latency (4 warps per chain)."""
-        _lib.check(self._L.stacb_set_mode(int(mode)), "stacb_set_mode")
+        """Scheduling of pose_clips (this handle): -1 auto, 0 throughput, 1 latency, 2 dense throughput, 3 wide latency."""
+        _lib.check(self._L.stacb_tree_set_mode(self._h, int(mode)), "stacb_tree_set_mode")
+
+    def set_path(self, path: int) -> None:
+        """0: register-resident hinge-tree solver where the model qualifies (default); 1: general kernels only."""
+        _lib.check(self._L.stacb_tree_set_path(self._h, int(path)), "stacb_tree_set_path")
+
+    @property
+    def path(self) -> int:
+        """1 when the register-resident solver serves this model, 0 for the general kernels."""
+        return int(self._L.stacb_tree_path(self._h))
 
     @property
     def smem_per_chain(self) -> int:
