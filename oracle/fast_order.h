@@ -11,7 +11,9 @@
  *     further hinges composed in the parent frame, world quaternions by pointer jumping, ONE rotation of each local offset by
  *     the parent's world quaternion, world positions by pointer jumping with plain additions;
  *   - rotate(v, q) = v + 2 (s t + u x t), t = u x v;
- *   - one site per lane: loss by the 32-lane butterfly, wrench prefix by Hillis-Steele over lanes;
+ *   - one site per lane (site p on lane p + 1, so the inclusive wrench scan doubles as the exclusive one): loss by the 32-lane
+ *     butterfly, wrench prefix by Hillis-Steele over lanes;
+ *   - sin / cos of the hinge half-angles up to a common sign (reduction by pi, no quadrant logic);
  *   - solver reductions: per-lane fma chain over the slots, then the butterfly; the passive coordinates enter the first
  *     line search through their own lane-dealt sum.
  * (JM, RT) is the kernel variant the dispatcher picks (first fit of (1,5,1), (3,4,3)): surplus slots / rounds are no-ops
@@ -23,7 +25,7 @@
 #define IDL 31
 
 typedef struct {
-  int JM, RT, n, K, has_free, free_adr, free_sa, free_se;
+  int JM, RT, n, K, has_free, free_e, free_adr;
   q4 Qc[LANES], Qs[LANES];
   v3 A[LANES], B[LANES], C[LANES], anc0[LANES], ax0[LANES];
   v3 jax[LANES][FJ], jpp[LANES][FJ], jcx[LANES][FJ], jps[LANES][FJ];
@@ -42,6 +44,25 @@ static inline v3 f_rotq(v3 v, q4 q) {
   v3 w = { r_fma(q.w, t.x, c.x), r_fma(q.w, t.y, c.y), r_fma(q.w, t.z, c.z) };
   v3 r = { r_fma(R(2), w.x, v.x), r_fma(R(2), w.y, v.y), r_fma(R(2), w.z, v.z) };
   return r;
+}
+
+/* (-1)^j (sin x, cos x), j = rint(x / pi): mirrors sincos_pi of csrc/stacb_math.cuh (the common sign cancels in FK) */
+static inline void f_sincos(REAL x, REAL *sp, REAL *cp) {
+  if (!IS_F32) { *sp = (REAL)sin(x); *cp = (REAL)cos(x); return; }
+  float xf = (float)x;
+  float j = rintf(xf * 0.318309873f);
+  float r = fmaf(-j, 3.14159274e+00f, xf);
+  r = fmaf(-j, -8.74227766e-08f, r);
+  r = fmaf(-j, -3.43024902e-15f, r);
+  float r2 = r * r;
+  float ps = fmaf(r2, 2.6056311526190257e-06f, -0.0001980953966267407f);
+  ps = fmaf(ps, r2, 0.008333065547049046f);
+  ps = fmaf(ps, r2, -0.16666659712791443f);
+  *sp = (REAL)fmaf(r * r2, ps, r);
+  float pc = fmaf(r2, -2.619248391511064e-07f, 2.4769240553723648e-05f);
+  pc = fmaf(pc, r2, -0.0013888567918911576f);
+  pc = fmaf(pc, r2, 0.041666656732559204f);
+  *cp = (REAL)fmaf(r2 * r2, pc, fmaf(-0.5f, r2, 1.0f));
 }
 
 static void fast_destroy(ofast *F) { if (F) { free(F->passive); free(F); } }
@@ -72,7 +93,7 @@ static ofast *fast_create(const omodel *m, const osched *s) {
   ofast *F = (ofast *)calloc(1, sizeof(ofast));
   F->JM = JM; F->RT = RT; F->n = s->nact; F->K = K; F->has_free = free_e >= 0;
   F->free_adr = free_e >= 0 ? m->jnt_qposadr[free_j] : 0;
-  F->free_sa = free_e >= 0 ? s->jnt_s[free_j] : 0; F->free_se = free_e >= 0 ? s->jnt_e[free_j] : 0;
+  F->free_e = free_e >= 0 ? free_e : 0;
   char *covered = (char *)calloc(m->nq + 1, 1);
   for (int l = 0; l < LANES; l++) {
     int on = l < s->nact, b = on ? s->act[l] : 0;
@@ -119,7 +140,7 @@ static ofast *fast_create(const omodel *m, const osched *s) {
     int live = j0 >= 0 && s->jnt_e[j0] > s->jnt_s[j0];
     F->sa[l] = live ? s->jnt_s[j0] : 0; F->se[l] = live ? s->jnt_e[j0] : 0;
     F->sk[l] = -1; F->seb[l] = IDL;
-    if (l < K) { F->sk[l] = s->site_order[l]; F->seb[l] = loc[m->site_body[s->site_order[l]]]; }
+    if (l >= 1 && l <= K) { F->sk[l] = s->site_order[l - 1]; F->seb[l] = loc[m->site_body[s->site_order[l - 1]]]; }  /* site p on lane p + 1 */
   }
   F->passive = (int *)calloc(m->nq + 1, sizeof(int));
   for (int i = 0; i < m->nq; i++) if (!covered[i]) F->passive[F->npassive++] = i;
@@ -162,7 +183,7 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
   v3 lp[LANES];
   for (int l = 0; l < LANES; l++) {
     REAL sh[FJ], ch[FJ];
-    for (int j = 0; j < JM; j++) c_sincos((pt[l][j] - F->ref[l][j]) * R(0.5), &sh[j], &ch[j]);
+    for (int j = 0; j < JM; j++) f_sincos((pt[l][j] - F->ref[l][j]) * R(0.5), &sh[j], &ch[j]);
     REAL ct = r_fma(ch[0], ch[0], -(sh[0] * sh[0])), sn = R(2) * (sh[0] * ch[0]);
     q4 quat = { r_fma(F->Qs[l].w, sh[0], F->Qc[l].w * ch[0]), r_fma(F->Qs[l].x, sh[0], F->Qc[l].x * ch[0]),
                 r_fma(F->Qs[l].y, sh[0], F->Qc[l].y * ch[0]), r_fma(F->Qs[l].z, sh[0], F->Qc[l].z * ch[0]) };
@@ -211,7 +232,7 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
 static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANES][FNS]) {
   const int JM = F->JM;
   v3 c = S->P[0];
-  REAL w[LANES][6], t2[LANES][6], ex[LANES + 1][6];
+  REAL w[LANES][6], t2[LANES][6], wrl[LANES][6];
   for (int l = 0; l < LANES; l++) {
     v3 f = { R(-2) * S->res[l].x, R(-2) * S->res[l].y, R(-2) * S->res[l].z };
     v3 tq = c_cross(sub3(S->s[l], c), f);
@@ -221,10 +242,10 @@ static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANE
     for (int l = 0; l < LANES; l++) for (int i = 0; i < 6; i++) t2[l][i] = (l >= off) ? w[l][i] + w[l - off][i] : w[l][i];
     memcpy(w, t2, sizeof(w));
   }
-  for (int i = 0; i < 6; i++) { ex[0][i] = R(0); for (int l = 1; l <= LANES; l++) ex[l][i] = w[l - 1][i]; }
+  /* site p sits on lane p + 1: the inclusive scan at lane l is the sum over the sites p < l */
   for (int l = 0; l < LANES; l++) {
-    REAL wr[6];
-    for (int i = 0; i < 6; i++) wr[i] = ex[F->se[l]][i] - ex[F->sa[l]][i];
+    REAL *wr = wrl[l];
+    for (int i = 0; i < 6; i++) wr[i] = w[F->se[l]][i] - w[F->sa[l]][i];
     v3 Fo = { wr[0], wr[1], wr[2] }, Tq = { wr[3], wr[4], wr[5] };
     v3 pp = S->P[F->par[l]];
     q4 pc = { S->Qp[l].w, -S->Qp[l].x, -S->Qp[l].y, -S->Qp[l].z };
@@ -235,8 +256,7 @@ static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANE
     g[l][JM] = R(0);
   }
   if (free_wanted) {
-    REAL wf[6];
-    for (int i = 0; i < 6; i++) wf[i] = ex[F->free_se][i] - ex[F->free_sa][i];
+    const REAL *wf = wrl[F->free_e];
     v3 Ff = { wf[0], wf[1], wf[2] }, Tw = { wf[3], wf[4], wf[5] };
     v3 Tf = sub3(Tw, c_cross(sub3(S->fpos, c), Ff));
     q4 qh = S->fq, tq = { 0, Tf.x, Tf.y, Tf.z };

@@ -119,10 +119,10 @@ __device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, in
 __device__ __forceinline__ void site_init(SiteC &st, const DevTree &T, int lane, const float *__restrict__ site_pos) {
   st.k = -1; st.eb = IDL; st.ef = 0;
   st.off = mk3(0.f, 0.f, 0.f); st.kp = mk3(0.f, 0.f, 0.f); st.km = mk3(0.f, 0.f, 0.f);
-  if (lane < T.K) {
-    st.k = __ldg(T.site_order + lane);
-    st.eb = __ldg(T.site_eact + lane);
-    st.ef = __ldg(T.site_efull + lane);
+  if (lane >= 1 && lane <= T.K) {
+    st.k = __ldg(T.site_order + lane - 1);
+    st.eb = __ldg(T.site_eact + lane - 1);
+    st.ef = __ldg(T.site_efull + lane - 1);
     if (site_pos) st.off = mk3(__ldg(site_pos + 3 * st.k), __ldg(site_pos + 3 * st.k + 1), __ldg(site_pos + 3 * st.k + 2));
   }
 }
@@ -152,7 +152,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &s
   }
   float sh[JM], ch[JM];
 #pragma unroll
-  for (int j = 0; j < JM; j++) sincos_canon((pt[j] - L.ref[j]) * 0.5f, &sh[j], &ch[j]);
+  for (int j = 0; j < JM; j++) sincos_pi((pt[j] - L.ref[j]) * 0.5f, &sh[j], &ch[j]);
   // first hinge, folded with the body's constant pose
   float ct = fmaf(ch[0], ch[0], -(sh[0] * sh[0])), sn = 2.0f * (sh[0] * ch[0]);
   Q4 quat = mk4(fmaf(L.Qs.w, sh[0], L.Qc.w * ch[0]), fmaf(L.Qs.x, sh[0], L.Qc.x * ch[0]), fmaf(L.Qs.y, sh[0], L.Qc.y * ch[0]),
@@ -190,10 +190,9 @@ __device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &s
 }
 
 // Reverse half: d loss / d (solver slots) at the point of the last eval_fwd<KEEP = true>.
-//   free_wanted: some coordinate of the free joint is optimised (uniform); free_sa / free_se: its sorted-site range.
+//   free_wanted: some coordinate of the free joint is optimised (uniform); free_e: lane of the free joint's body.
 template <int JM, int RT>
-__device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &S, int lane, bool free_wanted, int free_sa, int free_se,
-                                         float (&g)[JM + 1]) {
+__device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &S, int lane, bool free_wanted, int free_e, float (&g)[JM + 1]) {
   const V3 c = shfl3(S.P, 0);
   const V3 f = mk3(-2.0f * S.res.x, -2.0f * S.res.y, -2.0f * S.res.z);
   const V3 tq = cross3(sub3(S.s, c), f);
@@ -206,14 +205,11 @@ __device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &
       if (lane >= off) w[i] = w[i] + up;
     }
   }
-  float ex[6], wr[6];
+  // sites sit one lane up (site p on lane p + 1, lane 0 carries a zero wrench): the inclusive scan at lane l is the sum over
+  // the sites p < l, so a subtree's range [sa, se) is a difference of two scan values without an exclusive shift
+  float wr[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const float up = __shfl_up_sync(FULL, w[i], 1);
-    ex[i] = lane >= 1 ? up : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < 6; i++) wr[i] = __shfl_sync(FULL, ex[i], L.se) - __shfl_sync(FULL, ex[i], L.sa);
+  for (int i = 0; i < 6; i++) wr[i] = __shfl_sync(FULL, w[i], L.se) - __shfl_sync(FULL, w[i], L.sa);
   const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
   // the subtree wrench in the parent frame of the body, then every hinge slot of the body
   const V3 pp = shfl3(S.P, L.par);
@@ -225,9 +221,9 @@ __device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &
   for (int j = 1; j < JM; j++) g[j] = dot3(S.ax[j], sub3(Tp, cross3(S.anc[j], Fp)));
   g[JM] = 0.f;
   if (free_wanted) {  // uniform
-    float wf[6];
+    float wf[6];  // the free joint's subtree is its body's subtree: that lane's wrench
 #pragma unroll
-    for (int i = 0; i < 6; i++) wf[i] = __shfl_sync(FULL, ex[i], free_se) - __shfl_sync(FULL, ex[i], free_sa);
+    for (int i = 0; i < 6; i++) wf[i] = __shfl_sync(FULL, wr[i], free_e);
     const V3 Ff = mk3(wf[0], wf[1], wf[2]);
     const V3 Tf = sub3(mk3(wf[3], wf[4], wf[5]), cross3(sub3(S.fpos, c), Ff));
     float g4[4];
@@ -239,7 +235,8 @@ __device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &
   }
 }
 
-// Solver-side lane state.
+// Solver-side lane state.  Slots without a coordinate carry lb = ub = 0 and a masked (zero) gradient, so every solver
+// vector stays exactly zero there without a select.
 template <int NS>
 struct Slots {
   float lb[NS], ub[NS];
@@ -263,12 +260,35 @@ __device__ __forceinline__ void warp_sum2(float &a, float &b) {
   }
 }
 
+// FISTA momentum beta_k = (t_k - 1) / t_{k+1}, t_0 = 1, t_{k+1} = (1 + sqrt(1 + 4 t_k^2)) / 2 depends on the iteration number
+// only: the first BT values are tabulated once per CTA in shared memory ([BT] = t_BT for the iterations beyond the table).
+constexpr int BT = 512;
+__device__ __forceinline__ void beta_table_init(float *tbl) {  // one thread; callers synchronise the CTA afterwards
+  float t = 1.0f;
+  for (int k = 0; k < BT; k++) {
+    const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+    tbl[k] = (t - 1.0f) / tn;
+    t = tn;
+  }
+  tbl[BT] = t;
+}
+// momentum of iteration `it`; `t` is only carried beyond the table
+__device__ __forceinline__ float beta_of(const float *tbl, int it, float &t) {
+  if (it < BT) return tbl[it];
+  if (it == BT) t = tbl[BT];
+  const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
+  const float beta = (t - 1.0f) / tn;
+  t = tn;
+  return beta;
+}
+
 // Per-kernel constants every evaluation needs (registers).
 struct Uni {
-  int lane, free_sa, free_se;
+  int lane, free_e;
   bool has_free;
   float tol;
   int maxiter, maxls;
+  const float *betas;  // shared-memory momentum table (beta_table_init)
 };
 
 template <int JM>
@@ -314,21 +334,19 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
       rejected = (dec > cond + 1.1920929e-07f) && (halv < u.maxls);
     }
     if (!rejected) {
-      eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_sa, u.free_se, gt);
+      eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
 #pragma unroll
       for (int m = 0; m < NS; m++) gt[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? gt[m] : 0.f;
       if (in_ls) {  // accepted x+ = xn
         step = (stp <= 1e-6f) ? 1.0f : stp / 0.5f;
-        const float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
-        const float beta = (t - 1.0f) / tn;
+        const float beta = beta_of(u.betas, out.iters, t);
 #pragma unroll
         for (int m = 0; m < NS; m++) {
           y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
-          d[m] = co.valid[m] ? clipf(xn[m] - gt[m], co.lb[m], co.ub[m]) - xn[m] : 0.f;
+          d[m] = clipm(xn[m] - gt[m], co.lb[m], co.ub[m]) - xn[m];
           x[m] = xn[m];
         }
         out.err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
-        t = tn;
         out.iters++;
         sqp = 0.f;
         if (!(out.err > u.tol && out.iters < u.maxiter)) break;
@@ -347,7 +365,7 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
     }
 #pragma unroll
     for (int m = 0; m < NS; m++) {
-      xn[m] = co.valid[m] ? clipf(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      xn[m] = clipm(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]);
       d[m] = xn[m] - y[m];
     }
     sq = lane_dot<NS>(d, d);
@@ -389,12 +407,11 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
 #pragma unroll
   for (int m = 0; m < NS; m++) pt[m] = ((maskbits >> m) & 1u) ? y[m] : q0[m];
   float fy = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
-  eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_sa, u.free_se, g);
+  eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, g);
 #pragma unroll
   for (int m = 0; m < NS; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? g[m] : 0.f;
   float t = 1.0f, stp = 1.0f;
-  float tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
-  float beta = (t - 1.0f) / tn;
+  float beta = beta_of(u.betas, 0, t);
   int base = 0;
   for (;;) {
     float sj = stp;
@@ -403,7 +420,7 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     float sq = 0.f, dg = 0.f;
 #pragma unroll
     for (int m = 0; m < NS; m++) {
-      xj[m] = co.valid[m] ? clipf(fmaf(-sj, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      xj[m] = clipm(fmaf(-sj, g[m], y[m]), co.lb[m], co.ub[m]);
       d[m] = xj[m] - y[m];
       const float p = isY ? fmaf(beta, xj[m] - x[m], xj[m]) : xj[m];
       pt[m] = ((maskbits >> m) & 1u) ? p : q0[m];
@@ -415,7 +432,7 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
       sq = sq + sqp;
     }
     const float f = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
-    eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_sa, u.free_se, gt);
+    eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
 #pragma unroll
     for (int m = 0; m < NS; m++) gt[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? gt[m] : 0.f;
     if (!isY) {
@@ -423,7 +440,7 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
       const float cond = fmaf(sj, dg, 0.5f * sq);
       const bool rejected = (dec > cond + 1.1920929e-07f) && (base + j < u.maxls);
 #pragma unroll
-      for (int m = 0; m < NS; m++) d[m] = co.valid[m] ? clipf(xj[m] - gt[m], co.lb[m], co.ub[m]) - xj[m] : 0.f;
+      for (int m = 0; m < NS; m++) d[m] = clipm(xj[m] - gt[m], co.lb[m], co.ub[m]) - xj[m];
       const float err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
       if (u.lane == 0) {
         xc->acc[par][j] = rejected ? 0.f : 1.f;
@@ -456,7 +473,7 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     for (int i = 0; i < NC - 1; i++) sk = (i < k) ? sk * 0.5f : sk;
 #pragma unroll
     for (int m = 0; m < NS; m++) {
-      const float xk = co.valid[m] ? clipf(fmaf(-sk, g[m], y[m]), co.lb[m], co.ub[m]) : 0.f;
+      const float xk = clipm(fmaf(-sk, g[m], y[m]), co.lb[m], co.ub[m]);
       y[m] = fmaf(beta, xk - x[m], xk);
       x[m] = xk;
     }
@@ -464,11 +481,9 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     for (int m = 0; m < NS; m++) g[m] = xc->g[rp][k][32 * m + u.lane];
     fy = xc->fy[rp][k];
     out.err = xc->err[rp][k];
-    t = tn;
-    tn = 0.5f * (1.0f + sqrtf(fmaf(4.0f * t, t, 1.0f)));
-    beta = (t - 1.0f) / tn;
     stp = (sk <= 1e-6f) ? 1.0f : sk / 0.5f;
     out.iters++;
+    beta = beta_of(u.betas, out.iters, t);
     sqp = 0.f;
     if (!(out.err > u.tol && out.iters < u.maxiter)) break;
     base = 0;
@@ -530,7 +545,7 @@ __device__ __forceinline__ float passive_sq(const DevTree &T, int lane, const fl
   for (int i = lane; i < T.npassive; i += 32) {
     const int p = __ldg(T.passive + i);
     const float v = q[p];
-    const float d = clipf(v, lb[p], ub[p]) - v;
+    const float d = clipm(v, lb[p], ub[p]) - v;
     acc = first ? d * d : fmaf(d, d, acc);
     first = false;
   }
@@ -593,6 +608,9 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
   constexpr int NS = JM + 1;
   extern __shared__ float smem[];
   __shared__ int s_chain;
+  __shared__ float s_beta[BT + 1];
+  if (threadIdx.x == 0) beta_table_init(s_beta);
+  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int area = 2 * T.nqp + 7 * T.pqn;  // qbuf [nqp], (unused) [nqp], PQ [7 pqn]
   Chain ch(T, smem + (size_t)(COOP ? 0 : wib) * area, nullptr, lane, 0, 1, 0);
@@ -606,8 +624,8 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
   SlotAdr<JM> sa;
   slots_init<JM, RT>(co, sa, L, T, lane, a.lb, a.ub);
   Uni u;
-  u.lane = lane; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.free_e >= 0;
-  u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls;
+  u.lane = lane; u.free_e = T.free_e >= 0 ? T.free_e : 0; u.has_free = T.free_e >= 0;
+  u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls; u.betas = s_beta;
   const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P, npassive = T.npassive;
   const MaskSpec full_ms = {nullptr, nq}, root_ms = {nullptr, a.root_dims};
   const unsigned full_bits = slot_bits<JM>(co, sa, full_ms), root_bits = slot_bits<JM>(co, sa, root_ms);
@@ -666,7 +684,7 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
         if (writer)
           for (int i = lane; i < npassive; i += 32) {
             const int p = __ldg(T.passive + i);
-            if (mask_has(ms, p)) ch.qbuf[p] = clipf(ch.qbuf[p], a.lb[p], a.ub[p]);
+            if (mask_has(ms, p)) ch.qbuf[p] = clipm(ch.qbuf[p], a.lb[p], a.ub[p]);
           }
         if (COOP) __syncthreads(); else __syncwarp();
       }
@@ -699,6 +717,11 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
 template <int JM, int RT>
 __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a) {
   constexpr int NS = JM + 1;
+  __shared__ float s_beta[BT + 1];
+  if (a.mode == 2) {
+    if (threadIdx.x == 0) beta_table_init(s_beta);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   LaneC<JM, RT> L;
   lane_init<JM, RT>(L, T, lane);
@@ -709,8 +732,8 @@ __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a)
   SlotAdr<JM> sa;
   slots_init<JM, RT>(co, sa, L, T, lane, a.lb, a.ub);
   Uni u;
-  u.lane = lane; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.free_e >= 0;
-  u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls;
+  u.lane = lane; u.free_e = T.free_e >= 0 ? T.free_e : 0; u.has_free = T.free_e >= 0;
+  u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls; u.betas = s_beta;
   const int nq = T.nq, K = T.K;
   const MaskSpec ms = {a.q_mask, nq};
   const unsigned bits = slot_bits<JM>(co, sa, ms);
@@ -732,7 +755,7 @@ __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a)
       const float loss = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
       if (lane == 0) a.out_a[b] = loss;
       if (a.out_b) {
-        eval_bwd<JM, RT>(L, S, lane, free_wanted_of<JM>(u, bits), u.free_sa, u.free_se, g);
+        eval_bwd<JM, RT>(L, S, lane, free_wanted_of<JM>(u, bits), u.free_e, g);
         float *go = a.out_b + (size_t)b * nq;
         for (int i = lane; i < nq; i += 32) go[i] = 0.f;
         __syncwarp();
@@ -747,7 +770,7 @@ __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a)
       float *po = a.out_a + (size_t)b * nq;
       for (int i = lane; i < T.npassive; i += 32) {
         const int p = __ldg(T.passive + i);
-        po[p] = u.maxiter > 0 ? clipf(qb[p], a.lb[p], a.ub[p]) : qb[p];
+        po[p] = u.maxiter > 0 ? clipm(qb[p], a.lb[p], a.ub[p]) : qb[p];
       }
       slots_scatter<JM>(co, sa, x, po);
       if (lane == 0) { a.out_b[b] = so.err; a.iters[b] = so.iters; a.ls_evals[b] = so.ls; }

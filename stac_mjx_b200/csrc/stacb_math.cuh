@@ -80,6 +80,27 @@ __device__ __forceinline__ void sincos_canon(float x, float *sp, float *cp) {
   *cp = co;
 }
 
+// sin/cos up to a COMMON sign: 3-term Cody-Waite reduction by pi, then degree-9 / degree-8 minimax polynomials on
+// [-pi/2, pi/2] (sin within 2 ulp, cos within 1 ulp of 1).  Returns ((-1)^j sin x, (-1)^j cos x) with j = rint(x / pi):
+// a hinge's half-angle pair enters FK only through products of two of its members (cos t, sin t) and through the
+// quaternion (c, a s), whose overall sign does not change the rotation, so no quadrant logic is needed.
+// Identical bit for bit to the oracle's f_sincos (oracle/fast_order.h).
+__device__ __forceinline__ void sincos_pi(float x, float *sp, float *cp) {
+  const float j = rintf(x * 0.318309873f);
+  float r = fmaf(-j, 3.14159274e+00f, x);
+  r = fmaf(-j, -8.74227766e-08f, r);
+  r = fmaf(-j, -3.43024902e-15f, r);
+  const float r2 = r * r;
+  float ps = fmaf(r2, 2.6056311526190257e-06f, -0.0001980953966267407f);
+  ps = fmaf(ps, r2, 0.008333065547049046f);
+  ps = fmaf(ps, r2, -0.16666659712791443f);
+  *sp = fmaf(r * r2, ps, r);
+  float pc = fmaf(r2, -2.619248391511064e-07f, 2.4769240553723648e-05f);
+  pc = fmaf(pc, r2, -0.0013888567918911576f);
+  pc = fmaf(pc, r2, 0.041666656732559204f);
+  *cp = fmaf(r2 * r2, pc, fmaf(-0.5f, r2, 1.0f));
+}
+
 // math.axis_angle_to_quat
 __device__ __forceinline__ Q4 axis_angle(V3 a, float ang) {
   float s, c;
@@ -92,6 +113,9 @@ __device__ __forceinline__ float clipf(float x, float lo, float hi) {
   float t = (x > lo) ? x : lo;
   return (t < hi) ? t : hi;
 }
+
+// the same clip through the hardware min / max (one FMNMX each); differs from clipf at most in the sign of a zero
+__device__ __forceinline__ float clipm(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
