@@ -7,12 +7,14 @@
 // Mapping (fixed for the whole kernel, all state in registers, no shared memory inside an evaluation):
 //   lane e  <->  active body e (set order = body id order, parents first); lane 31 (and every lane >= n) is an IDENTITY
 //               element, so "no ancestor" needs no select: composing with the identity is exact;
-//   lane p  <->  marker site at sorted position p (sites sorted by body id, so a subtree is a contiguous range);
+//   lane p+1 <-> marker site at sorted position p (sites sorted by body id, so a subtree is a contiguous range; lane 0 carries
+//               a zero wrench, which makes the inclusive prefix scan over the lanes the exclusive one of the sites);
 //   solver  <->  slot j < JM of a lane is the angle of hinge j of the lane's body, slot JM of lanes 0..6 holds the seven
 //               coordinates of the free joint.  Coordinates of the model that are not in this layout ("passive": hinges
 //               outside the active subtree) have an identically zero gradient and never move (see solve).
 //
-// Canonical arithmetic of this path ("fast order", mirrored op for op by oracle/stac_oracle.c mode 2):
+// Canonical arithmetic of this path ("fast order"; the CPU oracle's mode 2 mirrors it op for op):
+//   * sin / cos of the hinge half-angles up to a common sign (reduction by pi, no quadrant logic: sincos_pi);
 //   * first hinge of a body folded with the body's constant pose: quat = Qc cos(h) + Qs sin(h), pos = A + B cos(t) + C sin(t),
 //     h = (q - ref)/2, cos t = cos^2 h - sin^2 h, sin t = 2 sin h cos h  (Qc, Qs, A, B, C derived once per lane);
 //   * further hinges of the same body composed in the parent frame: quat' = quat * ql, pos' = pos + R(quat)(jperp (1 - cos t) - (a x jpos) sin t);

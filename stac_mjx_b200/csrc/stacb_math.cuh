@@ -84,7 +84,7 @@ __device__ __forceinline__ void sincos_canon(float x, float *sp, float *cp) {
 // [-pi/2, pi/2] (sin within 2 ulp, cos within 1 ulp of 1).  Returns ((-1)^j sin x, (-1)^j cos x) with j = rint(x / pi):
 // a hinge's half-angle pair enters FK only through products of two of its members (cos t, sin t) and through the
 // quaternion (c, a s), whose overall sign does not change the rotation, so no quadrant logic is needed.
-// Identical bit for bit to the oracle's f_sincos (oracle/fast_order.h).
+// The CPU oracle's f_sincos is the same sequence of operations.
 __device__ __forceinline__ void sincos_pi(float x, float *sp, float *cp) {
   const float j = rintf(x * 0.318309873f);
   float r = fmaf(-j, 3.14159274e+00f, x);

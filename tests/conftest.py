@@ -26,7 +26,7 @@ class Case:
         self.K = len(self.kp_names)
         self.tol = float(self.cfg.model.FTOL)
 
-    def oracle(self, dtype=np.float32, mode=1):
+    def oracle(self, dtype=np.float32, mode=2):
         from oracle.oracle import Oracle
 
         return Oracle(self.tree, self.setup.site_bodies, dtype, mode)

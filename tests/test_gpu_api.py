@@ -34,7 +34,7 @@ def test_stac_core_seam_signatures(rodent):
     qs[:7] = True
     d2, res = core.q_opt(mdl, data, kp[0], qs, np.repeat(s.trunk_kps, 3), q0, s.lb, s.ub, s.site_idxs)
     assert d2 is data and res.params.shape == (rodent.tree.nq,)
-    ref = rodent.oracle(np.float32, 1).q_opt(q0.cpu().numpy(), s.lb, s.ub, qs, kp[0], np.repeat(s.trunk_kps, 3), s.initial_offsets, 1e-4)
+    ref = rodent.oracle(np.float32, 2).q_opt(q0.cpu().numpy(), s.lb, s.ub, qs, kp[0], np.repeat(s.trunk_kps, 3), s.initial_offsets, 1e-4)
     np.testing.assert_allclose(res.params.cpu().numpy(), ref[0], atol=1e-3)
     assert float(res.state.error) == pytest.approx(float(ref[1]), rel=1e-3)
     assert torch.equal(res.params[7:], q0[7:])  # masked-out coordinates stay at q0
@@ -47,7 +47,7 @@ def test_ik_only_matches_oracle_and_layout(rodent):
     kp, _, _ = rodent.session(C * F, F, seed=31)
     offsets = s.initial_offsets + 0.001
     d = st.ik_only(kp, offsets)
-    ref = rodent.oracle(np.float32, 1).pose_clips(kp.reshape(C, F, -1), rodent.tree.qpos0, offsets, s.lb, s.ub, s.indiv_parts, nthreads=4,
+    ref = rodent.oracle(np.float32, 2).pose_clips(kp.reshape(C, F, -1), rodent.tree.qpos0, offsets, s.lb, s.ub, s.indiv_parts, nthreads=4,
                                                   **rodent.root_kw())  # fmt: skip
     nb, K = rodent.tree.nbody, rodent.K
     assert d.qpos.shape == (C * F, rodent.tree.nq) and d.xpos.shape == (C * F, nb, 3) and d.xquat.shape == (C * F, nb, 4)
@@ -63,7 +63,7 @@ def test_fit_offsets_matches_oracle_driven_restatement(rodent):
     """Full alternation (root opt, N_ITERS x [pose pass, closed-form offsets], final pose pass; stac.py:254-354)."""
     F, n_iters = 8, 2
     st = make_stac(rodent, F, n_iters=n_iters)
-    s, o = rodent.setup, rodent.oracle(np.float32, 1)
+    s, o = rodent.setup, rodent.oracle(np.float32, 2)
     kp, _, _ = rodent.session(F, F, seed=77)
     d = st.fit_offsets(kp)
     # restatement of the same schedule on the oracle
@@ -109,7 +109,7 @@ def test_models_without_parts_or_root(engine_of):
         st = make_stac(c, F)
         kp, _, _ = c.session(2 * F, F, seed=5)
         d = st.ik_only(kp, c.setup.initial_offsets)
-        ref = c.oracle(np.float32, 1).pose_clips(kp.reshape(2, F, -1), c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub,
+        ref = c.oracle(np.float32, 2).pose_clips(kp.reshape(2, F, -1), c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub,
                                                  c.setup.indiv_parts, nthreads=4, **c.root_kw())  # fmt: skip
         np.testing.assert_allclose(d.qpos, ref["qpos"].reshape(2 * F, -1), atol=1e-3, rtol=0)
 

@@ -25,6 +25,12 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
+def E(g, key, path=0):
+    """Bit-level expectation for the kernels that serve the model: "g32_*" (oracle mode 2, fast order) where the
+    register-resident solver applies and the default path is used, "c32_*" (mode 1, canonical order) otherwise."""
+    return g[f"g32_{key}"] if path == 0 and f"g32_{key}" in g.files else g[f"c32_{key}"]
+
+
 @pytest.mark.parametrize("name", MODELS)
 def test_fk_matches_golden(name, engine_of):
     c, g = get_case(name), golden(name)
@@ -45,14 +51,14 @@ def test_loss_and_gradient_match_golden(name, engine_of):
     eng = engine_of(c)
     qm, km = np.ones(c.tree.nq, bool), np.ones(3 * c.K, bool)
     L, G = [npy(t) for t in eng.loss_grad(g["q"], g["q"], g["kp"][: len(g["q"])], qm, km, g["offsets"])]
-    np.testing.assert_allclose(L, g["c32_loss"], rtol=REL_TOL)
-    np.testing.assert_allclose(G, g["c32_grad"], atol=1e-5 * max(1.0, np.abs(g["c32_grad"]).max()))
+    np.testing.assert_allclose(L, E(g, "loss"), rtol=REL_TOL)
+    np.testing.assert_allclose(G, E(g, "grad"), atol=1e-5 * max(1.0, np.abs(E(g, "grad")).max()))
     np.testing.assert_allclose(G, g["f64_grad"], atol=1e-4 * max(1.0, np.abs(g["f64_grad"]).max()))
     L2, G2 = [npy(t) for t in eng.loss_grad(g["q"], g["q0"], g["kp"][: len(g["q"])], g["qm_part"], g["km_trunk"], g["offsets"])]
-    np.testing.assert_allclose(L2, g["c32_mloss"], rtol=REL_TOL)
-    np.testing.assert_allclose(G2, g["c32_mgrad"], atol=1e-5 * max(1.0, np.abs(g["c32_mgrad"]).max()))
+    np.testing.assert_allclose(L2, E(g, "mloss"), rtol=REL_TOL)
+    np.testing.assert_allclose(G2, E(g, "mgrad"), atol=1e-5 * max(1.0, np.abs(E(g, "mgrad")).max()))
     assert (G2[:, ~g["qm_part"].astype(bool)] == 0).all()  # masked-out coordinates have zero gradient
-    assert np.array_equal(G, g["c32_grad"]) and np.array_equal(L2, g["c32_mloss"]), "loss/grad no longer bit-identical"
+    assert np.array_equal(G, E(g, "grad")) and np.array_equal(L2, E(g, "mloss")), "loss/grad no longer bit-identical"
     Lonly, none = eng.loss_grad(g["q"], g["q"], g["kp"][: len(g["q"])], qm, km, g["offsets"], want_grad=False)
     assert none is None and np.array_equal(npy(Lonly), L)
 
@@ -64,11 +70,11 @@ def test_single_solves_match_golden(name, engine_of):
     n = len(g["c32_sol_iters"])
     p, e, it, ls = [npy(t) for t in eng.q_opt(g["q0"][:n], g["kp"][:n], g["root_mask"], g["km_trunk"], g["offsets"], c.setup.lb, c.setup.ub,
                                                float(g["tol"]), maxiter=50)]  # fmt: skip
-    np.testing.assert_array_equal(it, g["c32_sol_iters"])
-    np.testing.assert_array_equal(ls, g["c32_sol_ls"])
-    np.testing.assert_allclose(p, g["c32_sol_params"], atol=QPOS_TOL, rtol=0)
-    np.testing.assert_allclose(e, g["c32_sol_err"], rtol=REL_TOL)
-    assert np.array_equal(p, g["c32_sol_params"])
+    np.testing.assert_array_equal(it, E(g, "sol_iters"))
+    np.testing.assert_array_equal(ls, E(g, "sol_ls"))
+    np.testing.assert_allclose(p, E(g, "sol_params"), atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(e, E(g, "sol_err"), rtol=REL_TOL)
+    assert np.array_equal(p, E(g, "sol_params"))
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -81,18 +87,50 @@ def test_clips_match_golden(name, engine_of):
     out = eng.pose_clips(g["kp"].reshape(C, F, -1), qio, g["offsets"], c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
     o = {k: npy(v) for k, v in out.items()}
     assert (o["status"] == 0).all()
-    np.testing.assert_array_equal(o["iters"], g["c32_clip_iters"])
-    np.testing.assert_array_equal(o["ls_evals"], g["c32_clip_ls_evals"])
-    np.testing.assert_allclose(o["qpos"], g["c32_clip_qpos"], atol=QPOS_TOL, rtol=0)
-    np.testing.assert_allclose(o["sites"], g["c32_clip_sites"], atol=MARKER_TOL, rtol=0)
-    np.testing.assert_allclose(o["xpos"], g["c32_clip_xpos"], atol=MARKER_TOL, rtol=0)
-    np.testing.assert_allclose(o["err"], g["c32_clip_err"], rtol=REL_TOL)
-    np.testing.assert_array_equal(npy(qio), g["c32_clip_qpos"][:, -1])  # qpos_io carries the last frame's pose
+    np.testing.assert_array_equal(o["iters"], E(g, "clip_iters"))
+    np.testing.assert_array_equal(o["ls_evals"], E(g, "clip_ls_evals"))
+    np.testing.assert_allclose(o["qpos"], E(g, "clip_qpos"), atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(o["sites"], E(g, "clip_sites"), atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(o["xpos"], E(g, "clip_xpos"), atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(o["err"], E(g, "clip_err"), rtol=REL_TOL)
+    np.testing.assert_array_equal(npy(qio), E(g, "clip_qpos")[:, -1])  # qpos_io carries the last frame's pose
     for k in ("qpos", "xpos", "xquat", "sites", "err"):
-        assert np.array_equal(o[k], g[f"c32_clip_{k}"]), f"{k} no longer bit-identical to the canonical oracle"
+        assert np.array_equal(o[k], E(g, f"clip_{k}")), f"{k} no longer bit-identical to the canonical oracle"
 
 
-@pytest.mark.parametrize("name", ["rodent", "fly_treadmill", "mouse"])
+@pytest.mark.parametrize("name", ["rodent", "celegans", "synth_data"])
+def test_general_kernels_still_serve_the_fast_models(name, engine_of):
+    """Engine.set_path(1): the general kernels (canonical order, oracle mode 1) on the models the register-resident solver
+    serves by default -- loss / gradient, single solves and clips against the committed c32 vectors, bit for bit."""
+    c, g = get_case(name), golden(name)
+    eng = engine_of(c)
+    assert eng.path == 1
+    try:
+        eng.set_path(1)
+        assert eng.path == 0
+        qm, km = np.ones(c.tree.nq, bool), np.ones(3 * c.K, bool)
+        L, G = [npy(t) for t in eng.loss_grad(g["q"], g["q"], g["kp"][: len(g["q"])], qm, km, g["offsets"])]
+        assert np.array_equal(L, g["c32_loss"]) and np.array_equal(G, g["c32_grad"])
+        n = len(g["c32_sol_iters"])
+        p, e, it, ls = [npy(t) for t in eng.q_opt(g["q0"][:n], g["kp"][:n], g["root_mask"], g["km_trunk"], g["offsets"], c.setup.lb, c.setup.ub,
+                                                   float(g["tol"]), maxiter=50)]  # fmt: skip
+        assert np.array_equal(p, g["c32_sol_params"]) and np.array_equal(it, g["c32_sol_iters"])
+        C, F = g["c32_clip_qpos"].shape[:2]
+        for mode in (0, 1):
+            eng.set_mode(mode)
+            qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (C, 1)), device=eng.device)
+            out = eng.pose_clips(g["kp"].reshape(C, F, -1), qio, g["offsets"], c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
+            for k in ("qpos", "xpos", "xquat", "sites", "err", "iters", "ls_evals"):
+                assert np.array_equal(npy(out[k]), g[f"c32_clip_{k}"]), k
+    finally:
+        eng.set_path(0)
+        eng.set_mode(-1)
+    # the two paths agree to rounding on a single evaluation
+    np.testing.assert_allclose(g["g32_loss"], g["c32_loss"], rtol=1e-5)
+    np.testing.assert_allclose(g["g32_grad"], g["c32_grad"], atol=1e-5 * max(1.0, np.abs(g["c32_grad"]).max()))
+
+
+@pytest.mark.parametrize("name", ["rodent", "celegans", "fly_treadmill", "mouse"])
 def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
     """Throughput (0), latency (1: four cooperating warps, speculative line search), dense throughput (2) and grouped
     latency (3: three member warps per evaluation for wide trees; falls back to 1 for one-body-per-lane models) modes:
@@ -113,7 +151,7 @@ def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
         eng.set_mode(-1)
     for k in outs[0]:
         assert all(np.array_equal(outs[0][k], o[k]) for o in outs[1:]), k
-    ref = c.oracle(np.float32, 1).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
+    ref = c.oracle(np.float32, 2).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
                                               nthreads=4, **c.root_kw())  # fmt: skip
     np.testing.assert_allclose(outs[1]["qpos"], ref["qpos"], atol=QPOS_TOL, rtol=0)
     np.testing.assert_array_equal(outs[1]["iters"], ref["iters"])
@@ -128,7 +166,7 @@ def test_rodent_clip_against_live_oracle(rodent, engine_of):
     kp = kp.reshape(3, 12, -1)
     qio = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (3, 1)), device=eng.device)
     out = eng.pose_clips(kp, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
-    ref = rodent.oracle(np.float32, 1).pose_clips(kp, rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=4, **rodent.root_kw())
+    ref = rodent.oracle(np.float32, 2).pose_clips(kp, rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=4, **rodent.root_kw())
     np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
     np.testing.assert_array_equal(npy(out["root_stats"]), ref["root_stats"])
     np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
@@ -142,7 +180,7 @@ def test_rodent_clip_against_live_oracle(rodent, engine_of):
 def test_pose_without_root_and_warm_start_chain(rodent, engine_of):
     """fit_offsets-style use: do_root=0, second pass warm-started from qpos_io of the first."""
     eng = engine_of(rodent)
-    s, o = rodent.setup, rodent.oracle(np.float32, 1)
+    s, o = rodent.setup, rodent.oracle(np.float32, 2)
     kp, _, _ = rodent.session(5, 5, seed=9)
     kp = kp.reshape(1, 5, -1)
     qio = torch.tensor(rodent.tree.qpos0.astype(np.float32)[None], device=eng.device)
@@ -157,6 +195,35 @@ def test_pose_without_root_and_warm_start_chain(rodent, engine_of):
     np.testing.assert_array_equal(npy(b["iters"]), r2["iters"])
 
 
+def test_passive_coordinates_outside_their_box(rodent, engine_of):
+    """Hinges outside the active subtree have zero gradient: the first whole-body solve projects them into the box and
+    their move enters that solve's first line search (register-resident path: kept outside the solver slots)."""
+    eng = engine_of(rodent)
+    s = rodent.setup
+    kp, _, _ = rodent.session(8, 4, seed=77)
+    kp = kp.reshape(2, 4, -1)
+    q0 = np.tile(rodent.tree.qpos0.astype(np.float32), (2, 1))
+    q0[:, -1] += 10.0
+    q0[1, -5] -= 7.0
+    ref = rodent.oracle(np.float32, 2).pose_clips(kp, q0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=2, **rodent.root_kw())
+    try:
+        for mode in (0, 1, 3):
+            eng.set_mode(mode)
+            qio = torch.tensor(q0, device=eng.device)
+            out = eng.pose_clips(kp, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+            for k in ("qpos", "sites", "err", "iters", "ls_evals", "root_stats"):
+                assert np.array_equal(npy(out[k]), ref[k]), (mode, k)
+            assert (npy(out["qpos"])[..., -1] == s.ub[-1]).all()
+    finally:
+        eng.set_mode(-1)
+    p, e, it, ls = [npy(t) for t in eng.q_opt(q0, kp[:, 0], np.ones(rodent.tree.nq, bool), np.ones(3 * rodent.K, bool), s.initial_offsets,
+                                               s.lb, s.ub, 1e-4, maxiter=7)]  # fmt: skip
+    for i in range(2):
+        po, eo, ito, lso = rodent.oracle(np.float32, 2).q_opt(q0[i], s.lb, s.ub, np.ones(rodent.tree.nq, bool), kp[i, 0], np.ones(3 * rodent.K, bool),
+                                                               s.initial_offsets, 1e-4, maxiter=7)  # fmt: skip
+        assert np.array_equal(p[i], po) and (it[i], ls[i]) == (ito, lso)
+
+
 def test_edge_cases(rodent, engine_of):
     eng = engine_of(rodent)
     s = rodent.setup
@@ -164,7 +231,7 @@ def test_edge_cases(rodent, engine_of):
     # F = 1 clips, P = 0 (no part solves), root only (do_root=2)
     qio = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (4, 1)), device=eng.device)
     out = eng.pose_clips(kp.reshape(4, 1, -1), qio, s.initial_offsets, s.lb, s.ub, np.zeros((0, rodent.tree.nq), bool), **rodent.root_kw())
-    ref = rodent.oracle(np.float32, 1).pose_clips(kp.reshape(4, 1, -1), rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, [], **rodent.root_kw())
+    ref = rodent.oracle(np.float32, 2).pose_clips(kp.reshape(4, 1, -1), rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, [], **rodent.root_kw())
     assert out["iters"].shape == (4, 1, 1)
     np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
     q2 = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (4, 1)), device=eng.device)
@@ -270,7 +337,7 @@ def test_full_size_properties(rodent, engine_of):
     assert (a["err"][conv] <= rodent.tol).all()
     # oracle spot check on one full-length clip at full size
     ci = 17
-    ref = rodent.oracle(np.float32, 1).pose_clips(kp.reshape(C, F, -1)[ci : ci + 1], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub,
+    ref = rodent.oracle(np.float32, 2).pose_clips(kp.reshape(C, F, -1)[ci : ci + 1], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub,
                                                   s.indiv_parts, **rodent.root_kw())  # fmt: skip
     np.testing.assert_allclose(a["qpos"][ci], ref["qpos"][0], atol=QPOS_TOL, rtol=0)
     np.testing.assert_allclose(a["sites"][ci], ref["sites"][0], atol=MARKER_TOL, rtol=0)
@@ -284,12 +351,12 @@ def test_real_mocap_clip_matches_golden(rodent, engine_of):
     s = rodent.setup
     qio = torch.tensor(rodent.tree.qpos0.astype(np.float32)[None], device=eng.device)
     out = eng.pose_clips(g["kp"][None], qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
-    np.testing.assert_array_equal(npy(out["iters"])[0], g["c32_iters"])
-    np.testing.assert_array_equal(npy(out["root_stats"])[0], g["c32_root_stats"])
-    np.testing.assert_allclose(npy(out["qpos"])[0], g["c32_qpos"], atol=QPOS_TOL, rtol=0)
-    np.testing.assert_allclose(npy(out["sites"])[0], g["c32_sites"], atol=MARKER_TOL, rtol=0)
-    np.testing.assert_allclose(npy(out["err"])[0], g["c32_err"], rtol=REL_TOL)
-    assert np.array_equal(npy(out["qpos"])[0], g["c32_qpos"])
+    np.testing.assert_array_equal(npy(out["iters"])[0], E(g, "iters"))
+    np.testing.assert_array_equal(npy(out["root_stats"])[0], E(g, "root_stats"))
+    np.testing.assert_allclose(npy(out["qpos"])[0], E(g, "qpos"), atol=QPOS_TOL, rtol=0)
+    np.testing.assert_allclose(npy(out["sites"])[0], E(g, "sites"), atol=MARKER_TOL, rtol=0)
+    np.testing.assert_allclose(npy(out["err"])[0], E(g, "err"), rtol=REL_TOL)
+    assert np.array_equal(npy(out["qpos"])[0], E(g, "qpos"))
 
 
 def test_all_joint_types_on_gpu():
@@ -303,7 +370,8 @@ def test_all_joint_types_on_gpu():
     off = t.site_pos[site_idxs].astype(np.float32)
     K = len(sb)
     eng = Engine(t, sb, 0)
-    o = Oracle(t, sb, np.float32, 1)
+    o = Oracle(t, sb, np.float32, 2)
+    assert eng.path == 0 and not o.fast_path  # ball / slide joints: general kernels
     rng = np.random.default_rng(1)
     q = random_qpos(t, rng, 6).astype(np.float32)
     got = [npy(x) for x in eng.fk(q, off)]
@@ -361,7 +429,7 @@ def test_slide_root_model_uses_four_root_dofs():
     sb, off = t.site_bodyid[sidx], t.site_pos[sidx].astype(np.float32)
     lb, ub, _ = tree.align_joint_dims(t.jnt_type, t.jnt_range, t.jnt_names)
     assert int(t.jnt_type[0]) == 2 and t.nq == 5
-    eng, o = Engine(t, sb, 0), Oracle(t, sb, np.float32, 1)
+    eng, o = Engine(t, sb, 0), Oracle(t, sb, np.float32, 2)
     rng = np.random.default_rng(4)
     qt = rng.normal(scale=0.3, size=(2, 4, t.nq)).astype(np.float32)
     kp = np.stack([[o.fk(qt[c, f], off)[3].reshape(-1) for f in range(4)] for c in range(2)]).astype(np.float32)
@@ -384,7 +452,7 @@ def test_c_abi_without_torch(rodent):
     spec.loader.exec_module(demo)
     r = demo.run(n_clips=2, n_frames=3, seed=3)
     s = rodent.setup
-    ref = rodent.oracle(np.float32, 1).pose_clips(r["kp"], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=2,
+    ref = rodent.oracle(np.float32, 2).pose_clips(r["kp"], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=2,
                                                   **rodent.root_kw())  # fmt: skip
     np.testing.assert_array_equal(r["iters"], ref["iters"])
     np.testing.assert_allclose(r["qpos"], ref["qpos"], atol=QPOS_TOL, rtol=0)
@@ -399,7 +467,7 @@ def test_fly_tethered_config_against_live_oracle(engine_of):
     kp = kp.reshape(2, 5, -1)
     qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (2, 1)), device=eng.device)
     out = eng.pose_clips(kp, qio, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
-    ref = c.oracle(np.float32, 1).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
+    ref = c.oracle(np.float32, 2).pose_clips(kp, c.tree.qpos0, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts,
                                               nthreads=2, **c.root_kw())  # fmt: skip
     np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
     np.testing.assert_allclose(npy(out["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
@@ -433,7 +501,7 @@ def test_concurrent_launches_on_two_streams(rodent, engine_of):
 def test_large_batches_use_the_multi_warp_cta_path(rodent, engine_of):
     """B > 2 x SM count: four independent items per CTA in the batch kernel (fk / loss_grad / q_opt / m_stats)."""
     eng = engine_of(rodent)
-    s, o = rodent.setup, rodent.oracle(np.float32, 1)
+    s, o = rodent.setup, rodent.oracle(np.float32, 2)
     B = 700
     kp, qtrue, _ = rodent.session(B, B, seed=66)
     q = (qtrue + np.random.default_rng(0).normal(scale=0.02, size=qtrue.shape)).astype(np.float32)

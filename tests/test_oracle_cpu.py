@@ -166,12 +166,92 @@ def test_oracle_reproduces_golden_vectors(name):
             l, gr = o.loss_grad(g["q"][i], g["q"][i], qm, g["kp"][i], km, g["offsets"])
             np.testing.assert_allclose(l, g[f"{tag}_loss"][i], atol=tol, rtol=tol)
             np.testing.assert_allclose(gr, g[f"{tag}_grad"][i], atol=tol, rtol=0)
-    o = c.oracle(np.float32, 1)
     kw = c.root_kw()
     C, F = g["c32_clip_qpos"].shape[:2]
-    r = o.pose_clips(g["kp"].reshape(C, F, -1), c.tree.qpos0, g["offsets"], c.setup.lb, c.setup.ub, c.setup.indiv_parts, nthreads=4, **kw)
-    for k in ("qpos", "xpos", "xquat", "sites", "err", "iters", "ls_evals"):
-        np.testing.assert_array_equal(r[k], g[f"c32_clip_{k}"])
+    fast = c.oracle(np.float32, 2).fast_path
+    assert fast == ("g32_clip_qpos" in g.files) == (name in ("rodent", "celegans", "synth_data"))
+    for tag, mode in (("c32", 1),) + ((("g32", 2),) if fast else ()):
+        o = c.oracle(np.float32, mode)
+        r = o.pose_clips(g["kp"].reshape(C, F, -1), c.tree.qpos0, g["offsets"], c.setup.lb, c.setup.ub, c.setup.indiv_parts, nthreads=4, **kw)
+        for k in ("qpos", "xpos", "xquat", "sites", "err", "iters", "ls_evals"):
+            np.testing.assert_array_equal(r[k], g[f"{tag}_clip_{k}"])
+        for i in range(g[f"{tag}_loss"].shape[0]):
+            l, gr = o.loss_grad(g["q"][i], g["q"][i], qm, g["kp"][i], km, g["offsets"])
+            assert float(l) == float(g[f"{tag}_loss"][i])
+            np.testing.assert_array_equal(gr, g[f"{tag}_grad"][i])
+            l, gr = o.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
+            assert float(l) == float(g[f"{tag}_mloss"][i])
+            np.testing.assert_array_equal(gr, g[f"{tag}_mgrad"][i])
+    if not fast:  # mode 2 is mode 1 for the models the register-resident solver does not serve
+        r2 = c.oracle(np.float32, 2).pose_clips(g["kp"].reshape(C, F, -1), c.tree.qpos0, g["offsets"], c.setup.lb, c.setup.ub,
+                                                 c.setup.indiv_parts, nthreads=4, **kw)  # fmt: skip
+        np.testing.assert_array_equal(r2["qpos"], g["c32_clip_qpos"])
+
+
+# Mode 0 (the faithful restatement of MJX + jaxopt) is FROZEN: the digests below were taken when the goldens were first
+# committed and must never change when modes 1 / 2 follow a kernel change (tools/make_golden.py also reports drift).
+MODE0_DIGESTS = {
+    "rodent": "c162ee256d089aa2a7bb972c4300a37b",
+    "celegans": "2ebe18ab3f738af786ce5cae1321d194",
+    "fly_treadmill": "e20fe3b09e66f438d1d0f51b496b623a",
+    "synth_data": "0e7b57ad7d4e4ddd7b98ae5bc1de1e16",
+    "mouse": "b11191388fd6423c076acb0ad79fb183",
+    "rodent_real250": "d105185d2d6723bde419bf046fed2061",
+}
+
+
+@pytest.mark.parametrize("name", sorted(MODE0_DIGESTS))
+def test_mode0_goldens_are_frozen(name):
+    import hashlib
+
+    g = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+    h = hashlib.sha256()
+    for k in sorted(g.files):
+        if k.startswith("f64_") or k.startswith("m32_"):
+            h.update(k.encode())
+            h.update(np.ascontiguousarray(g[k]).tobytes())
+    assert h.hexdigest()[:32] == MODE0_DIGESTS[name], "the MJX-order (mode 0) golden vectors changed"
+
+
+def test_mode0_solver_output_is_frozen(rodent):
+    """The mode-0 code itself (not only its stored output): float64 and float32 MJX-order runs of the first frames of the
+    real clip reproduce the committed values (float64 to libm rounding, float32 exactly on this libm)."""
+    g = np.load(ROOT / "tests" / "golden" / "rodent_real250.npz")
+    s, n = rodent.setup, 6
+    for tag, dt, tol in (("f64", np.float64, 1e-9), ("m32", np.float32, 2e-3)):
+        r = rodent.oracle(dt, 0).pose_clips(g["kp"][None, :n], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+        np.testing.assert_array_equal(r["iters"][0][:, 1:], g[f"{tag}_iters"][:n, 1:])
+        np.testing.assert_allclose(r["qpos"][0], g[f"{tag}_qpos"][:n], atol=tol, rtol=0)
+
+
+@pytest.mark.parametrize("name", ["rodent", "celegans", "synth_data"])
+def test_fast_order_agrees_with_mjx_order(name):
+    """mode 2 (register-resident kernel arithmetic) vs mode 0: the same mathematics -- to 1e-12 in float64, to float32
+    rounding in float32 -- including the analytic gradient against reverse-mode autodiff and a solve that starts with
+    passive coordinates outside their box."""
+    c = get_case(name)
+    g = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
+    np.testing.assert_allclose(g["g32_loss"], g["f64_loss"], rtol=2e-4)
+    gs = np.abs(g["f64_grad"]).max()
+    np.testing.assert_allclose(g["g32_grad"], g["f64_grad"], atol=3e-5 * gs)
+    np.testing.assert_allclose(g["g32_mgrad"], g["f64_mgrad"], atol=3e-5 * max(np.abs(g["f64_mgrad"]).max(), 1e-9))
+    o0, o2 = c.oracle(np.float64, 0), c.oracle(np.float64, 2)
+    assert o2.fast_path
+    T = TorchModel(c.tree, c.setup.site_bodies)
+    for i in range(2):
+        a = o0.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
+        b = o2.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
+        L, G = T.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
+        assert abs(float(a[0]) - float(b[0])) < 1e-12 * max(1.0, float(a[0])) and abs(float(b[0]) - L) < 1e-12 * max(1.0, L)
+        np.testing.assert_allclose(b[1], a[1], atol=1e-11 * max(1.0, np.abs(a[1]).max()))
+        np.testing.assert_allclose(b[1], G, atol=2e-8 * max(1.0, np.abs(G).max()))
+    q0 = g["q0"][0].astype(np.float64).copy()
+    q0[-1] = c.setup.ub[-1] + 0.5 if np.isfinite(c.setup.ub[-1]) else q0[-1]  # outside the box (a passive hinge for the rodent)
+    qm, km = np.ones(c.tree.nq, bool), np.ones(3 * c.K, bool)
+    r0 = o0.q_opt(q0, c.setup.lb, c.setup.ub, qm, g["kp"][0], km, g["offsets"], 1e-9, maxiter=25)
+    r2 = o2.q_opt(q0, c.setup.lb, c.setup.ub, qm, g["kp"][0], km, g["offsets"], 1e-9, maxiter=25)
+    assert (r0[2], r0[3]) == (r2[2], r2[3])
+    np.testing.assert_allclose(r2[0], r0[0], atol=1e-9)
 
 
 @pytest.mark.parametrize("name", ["rodent", "celegans", "fly_treadmill", "mouse"])
@@ -235,9 +315,11 @@ def test_oracle_reproduces_real_mocap_clip(rodent):
     g = np.load(ROOT / "tests" / "golden" / "rodent_real250.npz")
     s = rodent.setup
     n = 25
-    r = rodent.oracle(np.float32, 1).pose_clips(g["kp"][None, :n], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
-    np.testing.assert_array_equal(r["qpos"][0], g["c32_qpos"][:n])
-    np.testing.assert_array_equal(r["iters"][0], g["c32_iters"][:n])
+    for tag, mode in (("c32", 1), ("g32", 2)):
+        r = rodent.oracle(np.float32, mode).pose_clips(g["kp"][None, :n], rodent.tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts,
+                                                       **rodent.root_kw())  # fmt: skip
+        np.testing.assert_array_equal(r["qpos"][0], g[f"{tag}_qpos"][:n])
+        np.testing.assert_array_equal(r["iters"][0], g[f"{tag}_iters"][:n])
 
 
 def test_all_joint_types_gradient_and_orders():

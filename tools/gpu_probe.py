@@ -14,7 +14,7 @@ kpn = list(cfg.model.KEYPOINT_MODEL_PAIRS.keys())
 s = model.make_setup(t, cfg.model, kpn)
 K = len(kpn)
 eng = Engine(t, s.site_bodies)
-orc = Oracle(t, s.site_bodies, np.float32, 1)
+orc = Oracle(t, s.site_bodies, np.float32, 2)
 off = s.initial_offsets
 F = 250
 kp, qtrue, _ = synth.synth_session(t, s, 4 * F, F)

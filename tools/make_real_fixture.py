@@ -1,6 +1,7 @@
 """tests/golden/rodent_real250.npz: the first 250 frames of the reference's real rat23 mocap fixture
 (tests/data/test_rodent_mocap_1000_frames.mat, BASELINE config 1) run through io.load_data with the rodent config,
-plus the oracle's IK output on them.  Needs /root/reference; run in the authoring container."""
+plus the oracle's IK output on them (c32 canonical order, g32 fast order = the default CUDA path, f64 / m32 MJX order in
+float64 / float32).  Needs /root/reference; run in the authoring container."""
 import sys
 from pathlib import Path
 import numpy as np
@@ -19,7 +20,7 @@ kp = kp[:250]
 s = model.make_setup(tree, cfg.model, names)
 kw = dict(do_root=1, root_kp_idx=s.root_kp_idx, trunk_kps=s.trunk_kps, tol=float(cfg.model.FTOL))
 out = {"kp": kp}
-for tag, dt, mode in (("c32", np.float32, 1), ("f64", np.float64, 0)):
+for tag, dt, mode in (("c32", np.float32, 1), ("g32", np.float32, 2), ("f64", np.float64, 0), ("m32", np.float32, 0)):
     r = Oracle(tree, s.site_bodies, dt, mode).pose_clips(kp[None], tree.qpos0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=1, **kw)
     for k in ("qpos", "sites", "err", "iters", "ls_evals", "root_stats"):
         out[f"{tag}_{k}"] = r[k][0]

@@ -16,7 +16,7 @@ for name in ("rodent", "celegans", "fly_treadmill", "fly_tethered", "synth_data"
     tree, cfg = model.load_fixture(name)
     kpn = list(cfg.model.KEYPOINT_MODEL_PAIRS.keys())
     s = model.make_setup(tree, cfg.model, kpn)
-    eng, orc = Engine(tree, s.site_bodies, 0), Oracle(tree, s.site_bodies, np.float32, 1)
+    eng, orc = Engine(tree, s.site_bodies, 0), Oracle(tree, s.site_bodies, np.float32, 2)
     has_root = s.root_kp_idx >= 0 and int(tree.jnt_type[0]) in (0, 2)
     kw = dict(do_root=1 if has_root else 0, root_kp_idx=s.root_kp_idx, trunk_kps=s.trunk_kps, tol=float(cfg.model.FTOL))
     for seed, noise in ((101, 1e-3), (202, 5e-3), (303, 2e-2)):
