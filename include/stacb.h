@@ -120,11 +120,32 @@ int stacb_pose_clips(const stacb_tree *tree, const float *kp, float *qpos_io, co
 
 /* _m_opt sufficient statistics over T frames (stac_core.py:146-159):
  *   s[k,i] = sum_t sum_j R_tk[j,i] (y_tk[j] - p_tk[j]),   z2 = sum_t sum_k |y_tk - p_tk|^2.
- *   kp [T,3K]  q [T,nq]  scratch [T,3K+1] (per-frame contributions)  s [K,3]  z2 [1]
- * Frames are reduced in index order (deterministic).  Ranks of a multi-GPU fit call this on
- * their frame shard and all-reduce (s, z2, T) before applying the closed form. */
-int stacb_m_stats(const stacb_tree *tree, const float *kp, const float *q, float *scratch, float *s, float *z2, int T,
-                  void *stream);
+ *   kp [T,3K]  q [T,nq]  scratch [stacb_m_scratch_floats(tree, T)]
+ *   out [3K+2] = { s[K,3], z2, (float)T }: ONE contiguous buffer, so the ranks of a multi-GPU fit all-reduce it in place
+ *   right behind this call on the same stream (3K+2 floats over NVLink) and apply the closed form redundantly.
+ * One kernel launch; frames are summed in a fixed order (chunks of 8 consecutive frames in frame order, then the chunk
+ * partials in chunk order): deterministic and independent of the grid. */
+int stacb_m_stats(const stacb_tree *tree, const float *kp, const float *q, float *scratch, float *out, int T, void *stream);
+
+/* Data term of the m-phase objective at the offsets m [K,3] (stac_core.py:160-165), evaluated from the residuals
+ *   out[0] = sum_t sum_k |y_tk - p_tk - R_tk m_k|^2
+ * instead of the reference's expanded form z2 - 2 sum(m s) + T sum(m^2): the same number without the cancellation of
+ * three O(z2) terms in float32 (the reference's identity-pose KAT asserts < 1e-8).  Same buffers and order as stacb_m_stats. */
+int stacb_m_residual(const stacb_tree *tree, const float *kp, const float *q, const float *m, float *scratch, float *out, int T,
+                     void *stream);
+int stacb_m_scratch_floats(const stacb_tree *tree, int T);
+
+/* Device epilogues of the IK pass (run on the packed device outputs before the single device-to-host copy).
+ *
+ * stacb_edge_crossfade -- utils.handle_edge_effects (stac_mjx/utils.py:393-461) for one packed array of `continuous` clips:
+ *   in [C, F+ov, D] -> out [stacb_edge_rows(C,F,ov), D]: the last ov frames of clip c are blended with the first ov frames of clip
+ *   c+1 ((1-w) a + w b in float64, rounded to float32 as numpy does), then first clip whole, middle clips [ov:], last clip [ov:-ov].
+ *   w [ov] float64 (device): the reference's sigmoid 0.5 (1 + tanh(10 (x - 0.5) / 2)), x = linspace(0, 1, ov).
+ * stacb_qvel -- utils.compute_velocity_from_kinematics (stac_mjx/utils.py:302-347) for C continuous clips:
+ *   qpos [C,F,nq] -> qvel [C,F,nv], nv = nq-1 with a free joint (first 7 qpos), else nq; the last frame of a clip gets zero velocity. */
+long long stacb_edge_rows(int C, int F, int ov);
+int stacb_edge_crossfade(const float *in, const double *w, float *out, int C, int F, int ov, int D, void *stream);
+int stacb_qvel(const float *qpos, float *qvel, int C, int F, int nq, int freejoint, float dt, float max_qvel, void *stream);
 
 /* Measurement helper for bench.py's FP32 roofline denominator: runs a dense FFMA loop
  * (blocks x threads, `iters` iterations of 16 independent FMAs per thread). out [blocks*threads]. */

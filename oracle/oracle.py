@@ -181,6 +181,13 @@ class Oracle:
         self.lib.oracle_m_stats(C.byref(self.m), self.mode, _p(kp), _p(q), T, _p(s), C.byref(z2))
         return s, self.dtype.type(z2.value)
 
+    def m_residual(self, kp, q, m):
+        """sum_t sum_k |y - p - R m|^2 (the data term of the m-phase objective at offsets m, from the residuals)."""
+        kp, q, m = self._f(kp), self._f(q), self._f(m, (self.K, 3))
+        out = self.real(0)
+        self.lib.oracle_m_residual(C.byref(self.m), self.mode, _p(kp), _p(q), _p(m), kp.shape[0], C.byref(out))
+        return self.dtype.type(out.value)
+
     def m_opt(self, kp, q, initial_offsets, is_regularized, reg_coef):
         """Closed-form offsets (reference stac_core.py:146-172)."""
         dt = self.dtype.type

@@ -790,46 +790,74 @@ int oracle_pose_clips(const omodel *m, int mode, const REAL *kp, int C, int F, c
   return 0;
 }
 
+/* mode >= 1 sums the frames in the order of the CUDA kernel: chunks of 8 consecutive frames in frame order, then the chunk
+ * partials in chunk order (csrc/stacb_device.cuh: m_phase_kernel).
+ * m != NULL: the data term of the objective at the offsets m instead,  z2_out = sum_t sum_k |y - p - R m|^2  (s_out unused). */
+#define MCH 8
+static int m_phase(const omodel *m, int mode, const REAL *kp, const REAL *q, const REAL *moff, int T, REAL *s_out, REAL *z2_out) {
+  int K = m->nsite, nq = m->nq;
+  osched *s = sched_create(m); owork *w = work_create(m);
+  REAL *tot = (REAL *)calloc(3 * K + 1, sizeof(REAL)), *part = (REAL *)calloc(3 * K + 1, sizeof(REAL));
+  for (int t = 0; t < T; t++) {
+    const REAL *qt = q + (size_t)t * nq, *yt = kp + (size_t)t * 3 * K;
+    int first = mode ? (t % MCH == 0) : (t == 0);
+    if (mode) fk_canon(m, s, s->act, s->nact, s->rounds_act, qt, w); else fk_mjx(m, s->act, s->nact, qt, w);
+    REAL zz[LANES]; for (int l = 0; l < LANES; l++) zz[l] = R(0);
+    REAL zf = R(0);
+    for (int pos = 0; pos < K; pos++) {
+      int k = mode ? s->site_order[pos] : pos, b = m->site_body[k];
+      q4 qb = ld4(w->Q + 4 * b); v3 p = ld3(w->P + 3 * b);
+      v3 z = { yt[3 * k] - p.x, yt[3 * k + 1] - p.y, yt[3 * k + 2] - p.z };
+      if (moff) {
+        v3 mk = ld3(moff + 3 * k);
+        v3 r = sub3(z, mode ? c_rotate(mk, qb) : m_rotate(mk, qb));
+        z = r;
+      } else {
+        /* math.quat_to_mat */
+        REAL ww = qb.w * qb.w, xx = qb.x * qb.x, yy = qb.y * qb.y, zq = qb.z * qb.z;
+        REAL xy = qb.x * qb.y, xz = qb.x * qb.z, yz = qb.y * qb.z, wx = qb.w * qb.x, wy = qb.w * qb.y, wz = qb.w * qb.z;
+        REAL M[3][3] = { { ww + xx - yy - zq, R(2) * (xy - wz), R(2) * (xz + wy) },
+                         { R(2) * (xy + wz), ww - xx + yy - zq, R(2) * (yz - wx) },
+                         { R(2) * (xz - wy), R(2) * (yz + wx), ww - xx - yy + zq } };
+        REAL zv[3] = { z.x, z.y, z.z };
+        for (int i = 0; i < 3; i++) {
+          REAL c = mode ? r_fma(M[2][i], zv[2], r_fma(M[1][i], zv[1], M[0][i] * zv[0])) : M[0][i] * zv[0] + M[1][i] * zv[1] + M[2][i] * zv[2];
+          part[3 * k + i] = first ? c : part[3 * k + i] + c;
+        }
+      }
+      if (mode) {
+        REAL e = r_fma(z.z, z.z, r_fma(z.y, z.y, z.x * z.x));
+        int l = pos / s->spl, i = pos % s->spl;
+        zz[l] = (i == 0) ? e : zz[l] + e;
+      } else zf = zf + (z.x * z.x + z.y * z.y + z.z * z.z);
+    }
+    if (mode) zf = butterfly32(zz);
+    part[3 * K] = first ? zf : part[3 * K] + zf;
+    if (mode && (t % MCH == MCH - 1 || t == T - 1)) {  /* chunk complete */
+      int c0 = (t / MCH) == 0;
+      for (int j = 0; j <= 3 * K; j++) tot[j] = c0 ? part[j] : tot[j] + part[j];
+    }
+  }
+  if (!mode) memcpy(tot, part, sizeof(REAL) * (3 * K + 1));
+  if (s_out && !moff) memcpy(s_out, tot, sizeof(REAL) * 3 * K);
+  *z2_out = tot[3 * K];
+  free(tot); free(part);
+  work_destroy(w); sched_destroy(s);
+  return 0;
+}
+
 /*
  * _m_opt sufficient statistics (stac_core.py:146-159): for T frames,
  *   s[k,i] = sum_t sum_j R_tk[j,i] * (y_tk[j] - p_tk[j]),  z2 = sum_t sum_k |y_tk - p_tk|^2
  * with p/R the world position / rotation matrix of each keypoint site's body.
  */
 int oracle_m_stats(const omodel *m, int mode, const REAL *kp, const REAL *q, int T, REAL *s_out, REAL *z2_out) {
-  int K = m->nsite, nq = m->nq;
-  osched *s = sched_create(m); owork *w = work_create(m);
-  for (int c = 0; c < 3 * K; c++) s_out[c] = R(0);
-  REAL z2 = R(0);
-  for (int t = 0; t < T; t++) {
-    const REAL *qt = q + (size_t)t * nq, *yt = kp + (size_t)t * 3 * K;
-    if (mode) fk_canon(m, s, s->act, s->nact, s->rounds_act, qt, w); else fk_mjx(m, s->act, s->nact, qt, w);
-    REAL zz[LANES]; for (int l = 0; l < LANES; l++) zz[l] = R(0);
-    for (int pos = 0; pos < K; pos++) {
-      int k = mode ? s->site_order[pos] : pos, b = m->site_body[k];
-      q4 qb = ld4(w->Q + 4 * b); v3 p = ld3(w->P + 3 * b);
-      v3 z = { yt[3 * k] - p.x, yt[3 * k + 1] - p.y, yt[3 * k + 2] - p.z };
-      /* math.quat_to_mat */
-      REAL ww = qb.w * qb.w, xx = qb.x * qb.x, yy = qb.y * qb.y, zq = qb.z * qb.z;
-      REAL xy = qb.x * qb.y, xz = qb.x * qb.z, yz = qb.y * qb.z, wx = qb.w * qb.x, wy = qb.w * qb.y, wz = qb.w * qb.z;
-      REAL M[3][3] = { { ww + xx - yy - zq, R(2) * (xy - wz), R(2) * (xz + wy) },
-                       { R(2) * (xy + wz), ww - xx + yy - zq, R(2) * (yz - wx) },
-                       { R(2) * (xz - wy), R(2) * (yz + wx), ww - xx - yy + zq } };
-      REAL zv[3] = { z.x, z.y, z.z };
-      for (int i = 0; i < 3; i++) {
-        REAL c = mode ? r_fma(M[2][i], zv[2], r_fma(M[1][i], zv[1], M[0][i] * zv[0])) : M[0][i] * zv[0] + M[1][i] * zv[1] + M[2][i] * zv[2];
-        s_out[3 * k + i] = s_out[3 * k + i] + c;
-      }
-      if (mode) {
-        REAL e = r_fma(z.z, z.z, r_fma(z.y, z.y, z.x * z.x));
-        int l = pos / s->spl, i = pos % s->spl;
-        zz[l] = (i == 0) ? e : zz[l] + e;
-      } else z2 = z2 + (z.x * z.x + z.y * z.y + z.z * z.z);
-    }
-    if (mode) z2 = z2 + butterfly32(zz);
-  }
-  *z2_out = z2;
-  work_destroy(w); sched_destroy(s);
-  return 0;
+  return m_phase(m, mode, kp, q, NULL, T, s_out, z2_out);
+}
+
+/* data term of the m-phase objective at the offsets moff [K,3], from the residuals */
+int oracle_m_residual(const omodel *m, int mode, const REAL *kp, const REAL *q, const REAL *moff, int T, REAL *out) {
+  return m_phase(m, mode, kp, q, moff, T, NULL, out);
 }
 
 int oracle_real_size(void) { return (int)sizeof(REAL); }

@@ -17,6 +17,11 @@ SYMBOLS = (
     "stacb_q_opt",
     "stacb_pose_clips",
     "stacb_m_stats",
+    "stacb_m_residual",
+    "stacb_m_scratch_floats",
+    "stacb_edge_rows",
+    "stacb_edge_crossfade",
+    "stacb_qvel",
     "stacb_fma_peak",
     "stacb_tree_set_mode",
     "stacb_tree_set_path",
@@ -76,7 +81,13 @@ def lib() -> C.CDLL:
         L.stacb_pose_clips.argtypes = (
             [vp] * 7 + [i32, i32, i32, vp, i32, f32, i32, i32] + [vp] * 9 + [i32, i32, vp]
         )
-        L.stacb_m_stats.argtypes = [vp] * 6 + [i32, vp]
+        L.stacb_m_stats.argtypes = [vp] * 5 + [i32, vp]
+        L.stacb_m_residual.argtypes = [vp] * 6 + [i32, vp]
+        L.stacb_m_scratch_floats.argtypes = [vp, i32]
+        L.stacb_edge_rows.argtypes = [i32, i32, i32]
+        L.stacb_edge_rows.restype = C.c_longlong
+        L.stacb_edge_crossfade.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+        L.stacb_qvel.argtypes = [vp, vp, i32, i32, i32, i32, f32, f32, vp]
         L.stacb_fma_peak.argtypes = [vp, i32, i32, i32, vp]
         L.stacb_tree_set_mode.argtypes = [vp, i32]
         L.stacb_tree_set_path.argtypes = [vp, i32]

@@ -22,6 +22,8 @@ for v in $FAST; do
 done
 $NVCC $FLAGS -c stacb_abi.cu -o _obj/abi.o > _obj/abi.log 2>&1 &
 pids="$pids $!"
+$NVCC $FLAGS -c stacb_post.cu -o _obj/post.o > _obj/post.log 2>&1 &
+pids="$pids $!"
 rc=0
 for p in $pids; do wait $p || rc=1; done
 cat _obj/*.log | grep -v -e '^ptxas info    : Function properties' -e 'bytes stack frame' -e '^ptxas info    : Compiling' -e '^ptxas info    : 0 bytes gmem' || true

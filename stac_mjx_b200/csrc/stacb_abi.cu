@@ -14,15 +14,6 @@
 
 namespace stacb {
 
-// Sequential (index-order) reduction of the per-frame m-phase contributions: one thread per output.
-__global__ void m_reduce_kernel(const float *__restrict__ contrib, int T, int n3k, float *__restrict__ s, float *__restrict__ z2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > n3k) return;
-  float acc = 0.f;
-  for (int t = 0; t < T; t++) acc = acc + contrib[(size_t)t * (n3k + 1) + c];
-  if (c < n3k) s[c] = acc; else z2[0] = acc;
-}
-
 __global__ void fma_peak_kernel(float *out, int iters) {
   float a[16];
 #pragma unroll
@@ -49,6 +40,9 @@ using namespace stacb;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+namespace stacb {
+int post_fail(int code, const char *msg) { return fail(code, msg); }
+}  // namespace stacb
 #define CUDA_TRY(expr)                                                                              \
   do {                                                                                              \
     cudaError_t e_ = (expr);                                                                        \
@@ -267,7 +261,8 @@ extern "C" int stacb_tree_smem_per_chain(const stacb_tree *t) { return t ? chain
 namespace stacb {
 #define X(c, n, f, p, j)                                                                                                    \
   cudaError_t launch_pose_##c##_##n##_##f##_##p##_##j(const DevTree &, const PoseArgs &, int, int, size_t, int, cudaStream_t); \
-  cudaError_t launch_batch_##c##_##n##_##f##_##p##_##j(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t);
+  cudaError_t launch_batch_##c##_##n##_##f##_##p##_##j(const DevTree &, const BatchArgs &, int, int, size_t, cudaStream_t); \
+  cudaError_t launch_mphase_##c##_##n##_##f##_##p##_##j(const DevTree &, const MArgs &, int, int, size_t, cudaStream_t);
 STACB_VARIANTS(X)
 #undef X
 #define X(j, r, f)                                                                                                   \
@@ -398,17 +393,43 @@ extern "C" int stacb_pose_clips(const stacb_tree *t, const float *kp, float *qpo
   return run_pose(t, a, (cudaStream_t)stream);
 }
 
-extern "C" int stacb_m_stats(const stacb_tree *t, const float *kp, const float *q, float *scratch, float *s_out, float *z2, int T,
-                             void *stream) {
-  if (!t || !kp || !q || !scratch || !s_out || !z2 || T < 0) return fail(STACB_E_INVALID, "stacb_m_stats: bad argument");
-  BatchArgs a{};
-  a.q = q; a.kp = kp; a.site_pos = nullptr; a.out_a = scratch; a.B = T; a.mode = 3;
-  int rc = run_batch(t, a, (cudaStream_t)stream);
-  if (rc) return rc;
-  const int n3k = 3 * t->T.K;
-  m_reduce_kernel<<<(n3k + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, T, n3k, s_out, z2);
-  CUDA_TRY(cudaGetLastError());
-  return STACB_OK;
+static int run_mphase(const stacb_tree *t, MArgs a, cudaStream_t s) {
+  DeviceGuard guard(t->device);
+  CUDA_TRY(guard.err);
+  a.ticket = t->counter + (t->next.fetch_add(1) % kCounterPool);
+  CUDA_TRY(cudaMemsetAsync(a.ticket, 0, sizeof(int), s));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  const int nchunk = (a.T + MCH - 1) / MCH;
+  const int wpb = 4;
+  const int grid = std::max(1, std::min((nchunk + wpb - 1) / wpb, sms * 4));
+  const size_t smem = (size_t)wpb * chain_smem_floats(t->T) * 4;
+  if (smem > 200 * 1024) return fail(STACB_E_UNSUPPORTED, "model needs too much shared memory per chain");
+#define X(c, n, f, p, j) \
+  if (fits(t, c, n, f, p, j)) { CUDA_TRY(launch_mphase_##c##_##n##_##f##_##p##_##j(t->T, a, grid, 32 * wpb, smem, s)); return STACB_OK; }
+  STACB_VARIANTS(X)
+#undef X
+  return fail(STACB_E_UNSUPPORTED, "model larger than every compiled kernel variant");
+}
+
+extern "C" int stacb_m_stats(const stacb_tree *t, const float *kp, const float *q, float *scratch, float *out, int T, void *stream) {
+  if (!t || !kp || !q || !scratch || !out || T < 0) return fail(STACB_E_INVALID, "stacb_m_stats: bad argument");
+  MArgs a{};
+  a.kp = kp; a.q = q; a.m = nullptr; a.scratch = scratch; a.out = out; a.T = T; a.mode = 0;
+  return run_mphase(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_m_residual(const stacb_tree *t, const float *kp, const float *q, const float *m, float *scratch, float *out, int T,
+                                void *stream) {
+  if (!t || !kp || !q || !m || !scratch || !out || T < 0) return fail(STACB_E_INVALID, "stacb_m_residual: bad argument");
+  MArgs a{};
+  a.kp = kp; a.q = q; a.m = m; a.scratch = scratch; a.out = out; a.T = T; a.mode = 1;
+  return run_mphase(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_m_scratch_floats(const stacb_tree *t, int T) {
+  if (!t || T < 0) return 0;
+  return std::max(1, (T + MCH - 1) / MCH) * (3 * t->T.K + 1);
 }
 
 extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream) {

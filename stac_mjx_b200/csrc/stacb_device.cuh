@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(MODE == 3 ? 128 * GRP : 128, MODE == 2 ? 4 : 1
 
 struct BatchArgs {
   const float *q, *q0, *kp, *site_pos, *lb, *ub; const uint8_t *q_mask, *kp_mask; float tol; int maxiter, maxls;
-  float *out_a, *out_b, *out_c, *out_d; int32_t *iters, *ls_evals; int B; int mode;  // 0 fk, 1 loss_grad, 2 q_opt, 3 m_stats
+  float *out_a, *out_b, *out_c, *out_d; int32_t *iters, *ls_evals; int B; int mode;  // 0 fk, 1 loss_grad, 2 q_opt
 };
 
 template <int CPL, int NB, int NBF, int SPL, int JMV = JM>
@@ -1137,7 +1137,7 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
         for (int m = 0; m < CPL; m++)
           if (co.valid[m]) a.out_b[(size_t)b * nq + lane + 32 * m] = g[m];
       }
-    } else if (a.mode == 2) {
+    } else {
       sites_load_kp<SPL>(st, a.kp + (size_t)b * 3 * K);
       sites_mask_u8<SPL>(st, a.kp_mask);
       const unsigned bits = mask_bits_u8<CPL>(ch, co, a.q_mask);
@@ -1147,16 +1147,51 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
       for (int m = 0; m < CPL; m++)
         if (co.valid[m]) a.out_a[(size_t)b * nq + lane + 32 * m] = x[m];
       if (lane == 0) { a.out_b[b] = so.err; a.iters[b] = so.iters; a.ls_evals[b] = so.ls; }
-    } else {
-      // m-phase per-frame contributions (stac_core.py:148-159): out_a[b][3K+1] = { R^T z per site, |z|^2 }
-      sites_load_kp<SPL>(st, a.kp + (size_t)b * 3 * K);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// m-phase (stac_core.py:146-165).  mode 0: sufficient statistics  s[k] = sum_t R_tk^T (y_tk - p_tk),  z2 = sum_t sum_k |y_tk - p_tk|^2;
+// mode 1: data term of the objective at given offsets m,  sum_t sum_k |y_tk - p_tk - R_tk m_k|^2  (no cancellation).
+// Fixed summation order: a warp sums a chunk of MCH consecutive frames in frame order, the chunk partials are summed in chunk order
+// by the last CTA to finish (ticket), so the result is reproducible and lands in ONE contiguous buffer { s[3K], z2, (float)T }
+// that a multi-GPU fit all-reduces in place right behind this kernel on the same stream.
+// ------------------------------------------------------------------------------------------
+constexpr int MCH = 8;
+struct MArgs { const float *kp, *q, *m; float *scratch, *out; int T, mode; int *ticket; };
+
+template <int CPL, int NB, int NBF, int SPL, int JMV = JM>
+__global__ void __launch_bounds__(128) m_phase_kernel(DevTree T, MArgs a) {
+  extern __shared__ float smem[];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  Chain ch(T, smem + (size_t)wib * role_smem_floats(T), smem + (size_t)wpb * role_smem_floats(T) + (size_t)wib * warp_smem_floats(T), lane, 0, 1, 1 + wib);
+  Coords<CPL> co;
+  coords_init<CPL>(ch, co, nullptr, nullptr);
+  Sites<SPL> st;
+  sites_init<SPL>(ch, st, a.mode == 1 ? a.m : nullptr);  // mode 1: st.off carries the offsets m
+  Hot<NB> H;
+  hot_init<NB>(H, ch);
+  const int nq = T.nq, K = T.K;
+  const int n3 = a.mode == 0 ? 3 * K + 1 : 1;
+  const int nchunk = (a.T + MCH - 1) / MCH;
+  for (int c = blockIdx.x * wpb + wib; c < nchunk; c += gridDim.x * wpb) {
+    V3 acc3[SPL];
+    float accz = 0.f;
+#pragma unroll
+    for (int i = 0; i < SPL; i++) acc3[i] = mk3(0.f, 0.f, 0.f);
+    const int t1 = min(a.T, (c + 1) * MCH);
+    for (int t = c * MCH; t < t1; t++) {
+      const bool first = t == c * MCH;
+      sites_load_kp<SPL>(st, a.kp + (size_t)t * 3 * K);
 #pragma unroll
       for (int m = 0; m < CPL; m++)
-        if (co.valid[m]) ch.qbuf[lane + 32 * m] = q[m];
+        if (co.valid[m]) ch.qbuf[lane + 32 * m] = a.q[(size_t)t * nq + lane + 32 * m];
       __syncwarp();
       FkState<NB> S;
       fk_hot<NB, false>(ch, H, S);
-      float acc = 0.f;
+      float e_lane = 0.f;
 #pragma unroll
       for (int i = 0; i < SPL; i++) {
         V3 p;
@@ -1164,25 +1199,52 @@ __global__ void __launch_bounds__(128) batch_kernel(DevTree T, BatchArgs a) {
         gather_pose<NB>(ch, S, st.k[i] >= 0 ? st.eact[i] : 0, p, qb);
         if (st.k[i] >= 0) {
           const V3 z = mk3(st.kp[i].x - p.x, st.kp[i].y - p.y, st.kp[i].z - p.z);
-          // math.quat_to_mat
-          const float ww = qb.w * qb.w, xx = qb.x * qb.x, yy = qb.y * qb.y, zz = qb.z * qb.z;
-          const float xy = qb.x * qb.y, xz = qb.x * qb.z, yz = qb.y * qb.z, wx = qb.w * qb.x, wy = qb.w * qb.y, wz = qb.w * qb.z;
-          const float M00 = ww + xx - yy - zz, M01 = 2.0f * (xy - wz), M02 = 2.0f * (xz + wy);
-          const float M10 = 2.0f * (xy + wz), M11 = ww - xx + yy - zz, M12 = 2.0f * (yz - wx);
-          const float M20 = 2.0f * (xz - wy), M21 = 2.0f * (yz + wx), M22 = ww - xx - yy + zz;
-          float *o3 = a.out_a + (size_t)b * (3 * K + 1) + 3 * st.k[i];
-          o3[0] = fmaf(M20, z.z, fmaf(M10, z.y, M00 * z.x));
-          o3[1] = fmaf(M21, z.z, fmaf(M11, z.y, M01 * z.x));
-          o3[2] = fmaf(M22, z.z, fmaf(M12, z.y, M02 * z.x));
-          const float e = fmaf(z.z, z.z, fmaf(z.y, z.y, z.x * z.x));
-          acc = (i == 0) ? e : acc + e;
+          float e;
+          if (a.mode == 0) {
+            // math.quat_to_mat
+            const float ww = qb.w * qb.w, xx = qb.x * qb.x, yy = qb.y * qb.y, zz = qb.z * qb.z;
+            const float xy = qb.x * qb.y, xz = qb.x * qb.z, yz = qb.y * qb.z, wx = qb.w * qb.x, wy = qb.w * qb.y, wz = qb.w * qb.z;
+            const float M00 = ww + xx - yy - zz, M01 = 2.0f * (xy - wz), M02 = 2.0f * (xz + wy);
+            const float M10 = 2.0f * (xy + wz), M11 = ww - xx + yy - zz, M12 = 2.0f * (yz - wx);
+            const float M20 = 2.0f * (xz - wy), M21 = 2.0f * (yz + wx), M22 = ww - xx - yy + zz;
+            const V3 cv = mk3(fmaf(M20, z.z, fmaf(M10, z.y, M00 * z.x)), fmaf(M21, z.z, fmaf(M11, z.y, M01 * z.x)),
+                              fmaf(M22, z.z, fmaf(M12, z.y, M02 * z.x)));
+            acc3[i] = first ? cv : add3(acc3[i], cv);
+            e = fmaf(z.z, z.z, fmaf(z.y, z.y, z.x * z.x));
+          } else {
+            const V3 r = sub3(z, rotate(st.off[i], qb));
+            e = fmaf(r.z, r.z, fmaf(r.y, r.y, r.x * r.x));
+          }
+          e_lane = (i == 0) ? e : e_lane + e;
         }
       }
-      const float z2 = warp_sum(acc);
-      if (lane == 0) a.out_a[(size_t)b * (3 * K + 1) + 3 * K] = z2;
+      const float ef = warp_sum(e_lane);
+      accz = first ? ef : accz + ef;
       __syncwarp();
     }
+    float *o = a.scratch + (size_t)c * n3;
+    if (a.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < SPL; i++)
+        if (st.k[i] >= 0) { o[3 * st.k[i]] = acc3[i].x; o[3 * st.k[i] + 1] = acc3[i].y; o[3 * st.k[i] + 2] = acc3[i].z; }
+    }
+    if (lane == 0) o[n3 - 1] = accz;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j < n3; j += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < nchunk; c++) {
+      const float v = __ldcg(a.scratch + (size_t)c * n3 + j);
+      acc = (c == 0) ? v : acc + v;
+    }
+    a.out[j] = acc;
+  }
+  if (a.mode == 0 && threadIdx.x == 0) a.out[n3] = (float)a.T;
 }
 
 }  // namespace stacb

@@ -35,4 +35,14 @@ cudaError_t FN(launch_batch_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T,
   return cudaGetLastError();
 }
 
+cudaError_t FN(launch_mphase_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T, const MArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+  auto k = m_phase_kernel<V_CPL, V_NB, V_NBF, V_SPL>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<grid, block, smem, s>>>(T, a);
+  return cudaGetLastError();
+}
+
 }  // namespace stacb

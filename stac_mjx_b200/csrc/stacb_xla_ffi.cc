@@ -134,11 +134,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(StacbFk, FkImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>());
 
 // _m_opt sufficient statistics; `scratch` is an extra result so XLA owns the temporary.
+// out [3K+2] = { s, z2, T }
 static ffi::Error MStatsImpl(cudaStream_t stream, int64_t tree, ffi::Buffer<ffi::F32> kp, ffi::Buffer<ffi::F32> q,
-                             ffi::ResultBuffer<ffi::F32> s, ffi::ResultBuffer<ffi::F32> z2, ffi::ResultBuffer<ffi::F32> scratch) {
+                             ffi::ResultBuffer<ffi::F32> out, ffi::ResultBuffer<ffi::F32> scratch) {
   const int T = static_cast<int>(kp.dimensions()[0]);
   return to_error(stacb_m_stats(reinterpret_cast<const stacb_tree *>(tree), kp.typed_data(), q.typed_data(), scratch->typed_data(),
-                                s->typed_data(), z2->typed_data(), T, stream));
+                                out->typed_data(), T, stream));
 }
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(StacbMStats, MStatsImpl,
@@ -147,6 +148,5 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(StacbMStats, MStatsImpl,
                                   .Attr<int64_t>("tree")
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>());

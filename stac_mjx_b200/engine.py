@@ -167,14 +167,62 @@ class Engine:
         return out
 
     # -- stac_core._m_opt sufficient statistics ------------------------------
-    def m_stats(self, kp, q):
+    def _m_scratch(self, T: int) -> torch.Tensor:
+        return self.empty(int(self._L.stacb_m_scratch_floats(self._h, int(T))))
+
+    def m_stats_buffer(self, kp, q) -> torch.Tensor:
+        """One contiguous device buffer [3K+2] = { s[K,3], z2, float(T) } (all-reduced in place by multi-GPU fits)."""
         kp, q = self.f32(kp), self.f32(q)
         T = int(kp.shape[0])
-        scratch = self.empty(max(T, 1), 3 * self.K + 1)
-        s, z2 = self.empty(self.K, 3), self.empty(1)
-        rc = self._L.stacb_m_stats(self._h, _ptr(kp), _ptr(q), _ptr(scratch), _ptr(s), _ptr(z2), T, self._stream())
+        out = self.empty(3 * self.K + 2)
+        rc = self._L.stacb_m_stats(self._h, _ptr(kp), _ptr(q), _ptr(self._m_scratch(T)), _ptr(out), T, self._stream())
         _lib.check(rc, "stacb_m_stats")
-        return s, z2
+        return out
+
+    def m_stats(self, kp, q):
+        out = self.m_stats_buffer(kp, q)
+        return out[: 3 * self.K].reshape(self.K, 3), out[3 * self.K : 3 * self.K + 1]
+
+    def m_residual(self, kp, q, m) -> torch.Tensor:
+        """sum_t sum_k |y - p - R m|^2 at the offsets m [K,3]: device tensor [1]."""
+        kp, q, m = self.f32(kp), self.f32(q), self.f32(m, (self.K, 3))
+        T = int(kp.shape[0])
+        out = self.empty(1)
+        rc = self._L.stacb_m_residual(self._h, _ptr(kp), _ptr(q), _ptr(m), _ptr(self._m_scratch(T)), _ptr(out), T, self._stream())
+        _lib.check(rc, "stacb_m_residual")
+        return out
+
+    # -- device epilogues of the IK pass (utils.handle_edge_effects / compute_velocity_from_kinematics) ----------
+    def edge_crossfade(self, packed: torch.Tensor, n_frames_per_clip: int, overlap: int) -> torch.Tensor:
+        """`packed` [C * (F + ov), ...] (any trailing shape) -> [rows, ...] with the overlaps cross-faded and removed."""
+        F, ov = int(n_frames_per_clip), int(overlap)
+        x = self.f32(packed)
+        tail = tuple(x.shape[1:])
+        D = int(np.prod(tail)) if tail else 1
+        C = x.shape[0] // (F + ov)
+        if C * (F + ov) != x.shape[0]:
+            raise ValueError("packed length is not a multiple of n_frames_per_clip + overlap")
+        rows = int(self._L.stacb_edge_rows(C, F, ov))
+        if rows < 0:
+            raise ValueError("edge_crossfade: need at least one clip and n_frames_per_clip >= overlap")
+        xs = np.linspace(0.0, 1.0, ov)
+        w = torch.as_tensor(0.5 * (1.0 + np.tanh(10.0 * (xs - 0.5) / 2.0)), dtype=torch.float64).to(self.device)
+        out = self.empty(rows, *tail)
+        rc = self._L.stacb_edge_crossfade(_ptr(x), _ptr(w), _ptr(out), C, F, ov, D, self._stream())
+        _lib.check(rc, "stacb_edge_crossfade")
+        return out
+
+    def qvel(self, qpos: torch.Tensor, n_frames_per_clip: int, dt: float, freejoint: bool = True, max_qvel: float = 20.0) -> torch.Tensor:
+        """qpos [C * F, nq] of C continuous clips -> qvel [C * F, nv]."""
+        q = self.f32(qpos)
+        F = int(n_frames_per_clip)
+        C, nq = q.shape[0] // F, int(q.shape[-1])
+        if C * F != q.shape[0]:
+            raise ValueError("qpos length is not a multiple of n_frames_per_clip")
+        out = self.empty(C * F, nq - 1 if freejoint else nq)
+        rc = self._L.stacb_qvel(_ptr(q), _ptr(out), C, F, nq, int(bool(freejoint)), float(dt), float(max_qvel), self._stream())
+        _lib.check(rc, "stacb_qvel")
+        return out
 
     def fma_peak_tflops(self, iters: int = 20000) -> float:
         """Measured FP32 FMA throughput (TFLOP/s) of this GPU: bench.py's roofline denominator."""

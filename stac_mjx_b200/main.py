@@ -41,17 +41,11 @@ def _fit_phase(stac: Stac, cfg, kp_data, out_path: Path) -> None:
 def _ik_phase(stac: Stac, kp_data, fit_path: Path, out_path: Path, t0: float) -> None:
     print("Running ik_only()")
     cfg, fitted = io.load_stac_data(fit_path)  # the stored config replaces the live one, as in the reference (main.py:111-113)
-    result = stac.ik_only(kp_data, fitted.offsets)
+    # the reference cross-fades and differentiates on the host afterwards (main.py:118-133); here both are device epilogues of the IK pass
     if cfg.stac.continuous:
         print("Handling edge effects...")
-        result = utils.handle_edge_effects(result, cfg.stac.n_frames_per_clip)
+    result = stac.ik_only(kp_data, fitted.offsets, edge_effects=bool(cfg.stac.continuous), infer_qvels=bool(cfg.stac.get("infer_qvels", False)))
     print(f"Final qpos shape: {result.qpos.shape}")
-    if cfg.stac.get("infer_qvels", False):
-        import numpy as np
-
-        clips = result.qpos.reshape((-1, cfg.stac.n_frames_per_clip, result.qpos.shape[-1]))
-        dt = float(stac._mj_model.opt.timestep)
-        result.qvel = np.concatenate([utils.compute_velocity_from_kinematics(c, dt, freejoint=stac._freejoint) for c in clips], axis=0)
     print(f"Saving data to {out_path}. Finished in {(time.time() - t0) / 60:.2f} minutes")
     io.save_data_to_h5(config=cfg, file_path=out_path, **result.as_dict())
 

@@ -26,15 +26,13 @@ def shard_range(n: int, rank: int, world_size: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allreduce_m_stats(s: torch.Tensor, z2: torch.Tensor, T: int):
-    """Sum the m-phase sufficient statistics over ranks: one collective of 3K+2 floats."""
+def allreduce_m_stats(buf: torch.Tensor) -> torch.Tensor:
+    """Sum a flat m-phase buffer over ranks IN PLACE: ``[s (3K), z2, T]`` (3K+2 floats, one NCCL all-reduce on the stream
+    the statistics kernel ran on) or the 1-float residual of the objective."""
     rank, ws = world()
-    if ws == 1:
-        return s, z2, T
-    buf = torch.cat([s.reshape(-1), z2.reshape(-1), torch.tensor([float(T)], device=s.device, dtype=s.dtype)])
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-    n = s.numel()
-    return buf[:n].reshape(s.shape), buf[n : n + 1], int(round(float(buf[n + 1])))
+    if ws > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf
 
 
 def allgather_blocks(local: torch.Tensor, n_total: int) -> torch.Tensor:

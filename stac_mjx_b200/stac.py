@@ -140,7 +140,7 @@ class Stac:
         tidx_all = self.time_indices
         if tidx_all is None:
             tidx_all = compute_stac.sample_time_indices(C * F, int(self.cfg.model.N_SAMPLE_FRAMES))
-        tidx_all = np.sort(np.asarray(tidx_all))
+        tidx_all = np.asarray(tidx_all)  # kept in the sample's own order: the statistics are summed in this order
         mine = tidx_all[(tidx_all >= lo * F) & (tidx_all < hi * F)] - lo * F  # this rank's share of the frame sample
         mjx_model = stac_core.StacModel(engine=eng, site_pos=eng.f32(self._offsets, (eng.K, 3)))
         out = None
@@ -177,14 +177,20 @@ class Stac:
         )  # fmt: skip
 
     # ------------------------------------------------------------------
-    def ik_only(self, kp_data, offsets) -> io.StacData:
+    def ik_only(self, kp_data, offsets, *, edge_effects: bool = False, infer_qvels: bool = False) -> io.StacData:
         """Inverse kinematics with fixed offsets over independent clips (reference ``stac.py:356-454``).
 
         The reference vmaps ``root_optimization`` and ``pose_optimization`` over clips; here the whole phase is ONE
         fused launch (``stacb_pose_clips`` with ``do_root=1``) on this rank's block of clips.  Outputs are produced
         directly in the reference's packed layout (``_package_data(batched=True)``, ``stac.py:483-486``): qpos / xpos /
         xquat clip-major -- which is the kernel's native layout -- and marker_sites frame-major (transposed on the GPU).
+
+        ``edge_effects`` / ``infer_qvels`` (keyword extensions; the reference does both on the host afterwards,
+        ``main.py:118-133``) run ``utils.handle_edge_effects`` and ``utils.compute_velocity_from_kinematics`` as device
+        epilogues on the packed outputs before the single device-to-host copy.
         """
+        _nvtx = torch.cuda.nvtx
+        _nvtx.range_push("stac.ik_only/h2d")
         kp_data = np.asarray(kp_data, dtype=np.float32)
         batched_kp_data = utils.batch_kp_data(kp_data, self.cfg.stac.n_frames_per_clip, continuous=self.cfg.stac.continuous)
         eng = self._engine
@@ -204,11 +210,14 @@ class Stac:
         elif self._fixed:
             print("ROOT_OPTIMIZATION_KEYPOINT specified but model has fixed root, skipping root_optimization()")
         q = self.stac_core_obj.q_solver
+        _nvtx.range_pop()
+        _nvtx.range_push("stac.ik_only/pose_clips")
         out = eng.pose_clips(
             kp_dev, qio, site_pos, self._lb, self._ub, self._indiv_parts, do_root=1 if has_root else 0,
             root_kp_idx=max(self._root_kp_idx, 0), trunk_kps=self._trunk_kps, root_dims=4 if self._slidejoint else 7,
             tol=q.tol, maxiter=q.maxiter, maxls=q.maxls,
         )  # fmt: skip
+        _nvtx.range_pop()
         self.last_stats = {"iters": out["iters"], "ls_evals": out["ls_evals"], "status": out["status"], "root_stats": out["root_stats"]}
         res = {k: out[k] for k in ("qpos", "xpos", "xquat", "sites", "err")}
         if ws > 1:  # hand every rank the complete result (blocks are contiguous in the clip-major layout)
@@ -221,20 +230,39 @@ class Stac:
             "marker_sites": res["sites"].transpose(0, 1).reshape(C * F, K, 3),  # frame-major interleave (stac.py:486)
             "err": res["err"],
         }
+        kp_packed = batched_kp_data.reshape(-1, batched_kp_data.shape[-1])
+        if edge_effects:  # device epilogue: sigmoid cross-fade of the look-ahead overlap, overlaps removed (utils.py:393-461)
+            if not self.cfg.stac.continuous:
+                raise ValueError("edge_effects needs cfg.stac.continuous clips (the overlap is what is cross-faded)")
+            _nvtx.range_push("stac.ik_only/edge_crossfade")
+            Fc, ov = int(self.cfg.stac.n_frames_per_clip), utils.CONTINUOUS_BATCH_OVERLAP
+            for k in ("qpos", "xpos", "xquat", "marker_sites"):
+                dev[k] = eng.edge_crossfade(dev[k].contiguous(), Fc, ov)
+            kp_packed = utils.edge_crossfade_host(kp_packed, Fc)
+            _nvtx.range_pop()
+        if infer_qvels:  # device epilogue: finite-difference velocities per clip (utils.py:302-347)
+            _nvtx.range_push("stac.ik_only/qvel")
+            dev["qvel"] = eng.qvel(dev["qpos"].contiguous(), int(self.cfg.stac.n_frames_per_clip), float(self._mj_model.opt.timestep), self._freejoint)
+            _nvtx.range_pop()
+        _nvtx.range_push("stac.ik_only/d2h")
         host = {}
-        for k, v in dev.items():  # the step's D2H read, through pinned buffers
-            buf = self._pinned("out_" + k, tuple(v.shape), v.dtype)
+        for k, v in dev.items():  # the step's D2H read: ONE copy into page-locked arrays that the returned StacData owns
+            buf = self._pinned_out("out_" + k, tuple(v.shape), v.dtype)
             buf.copy_(v, non_blocking=True)
             host[k] = buf
         torch.cuda.synchronize(eng.device)
-        _, mean, std = self._get_error_stats(host["err"].numpy())
+        _nvtx.range_pop()
+        arrays = {k: self._hand_out("out_" + k, host[k]) for k in host}
+        _, mean, std = self._get_error_stats(arrays["err"])
         print(f"Mean: {mean}")
         print(f"Standard deviation: {std}")
-        return io.StacData(
-            qpos=host["qpos"].numpy().copy(), xpos=host["xpos"].numpy().copy(), xquat=host["xquat"].numpy().copy(),
-            marker_sites=host["marker_sites"].numpy().copy(), offsets=np.array(offsets), names_qpos=self._part_names,
-            names_xpos=self._body_names, kp_data=batched_kp_data.reshape(-1, batched_kp_data.shape[-1]), kp_names=self._kp_names,
+        data = io.StacData(
+            qpos=arrays["qpos"], xpos=arrays["xpos"], xquat=arrays["xquat"], marker_sites=arrays["marker_sites"], offsets=np.array(offsets),
+            names_qpos=self._part_names, names_xpos=self._body_names, kp_data=kp_packed, kp_names=self._kp_names,
         )  # fmt: skip
+        if infer_qvels:
+            data.qvel = arrays["qvel"]
+        return data
 
     def _pinned(self, key: str, shape, dtype) -> torch.Tensor:
         """Reusable page-locked host buffer (allocating pinned memory per call would dominate small sessions)."""
@@ -244,6 +272,22 @@ class Stac:
             buf = torch.empty(tuple(shape), dtype=dtype).pin_memory() if int(np.prod(shape)) else torch.empty(tuple(shape), dtype=dtype)
             cache[key] = buf
         return buf
+
+    def _pinned_out(self, key: str, shape, dtype) -> torch.Tensor:
+        """Page-locked OUTPUT buffer.  The numpy view handed to the caller (`_hand_out`) aliases it, so it is reused by a later call
+        only once every array derived from that view has been released; otherwise a fresh buffer is allocated (no copy either way)."""
+        live = self.__dict__.setdefault("_pin_out_live", {})
+        ref = live.get(key)
+        if ref is not None and ref() is not None:  # the previous result is still referenced by the caller
+            self.__dict__.setdefault("_pin_cache", {}).pop(key, None)
+        return self._pinned(key, shape, dtype)
+
+    def _hand_out(self, key: str, buf: torch.Tensor) -> np.ndarray:
+        import weakref
+
+        arr = buf.numpy()
+        self.__dict__.setdefault("_pin_out_live", {})[key] = weakref.ref(arr)
+        return arr
 
     # ------------------------------------------------------------------
     def _package_data(self, mjx_model, qposes, xposes, xquats, marker_sites, kp_data, batched: bool = False) -> io.StacData:

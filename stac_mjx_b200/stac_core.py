@@ -93,24 +93,30 @@ def _q_opt(q_solver, mjx_model, mjx_data, marker_ref_arr, qs_to_opt, kps_to_opt,
 def _m_opt(mjx_model, mjx_data, keypoints, q, initial_offsets, is_regularized, reg_coef, site_idxs=None, reduce_fn=None):
     """Closed-form marker offsets (reference ``stac_core.py:102-172``).
 
-    The GPU produces the sufficient statistics ``s``, ``z2``; ``reduce_fn(s, z2, T)``, when given,
-    all-reduces them across ranks (m-phase of a multi-GPU fit) before the closed form is applied.
+    One kernel produces the sufficient statistics as ONE device buffer ``[s (3K), z2, T]``; ``reduce_fn(buf)``, when
+    given, all-reduces it in place across ranks (m-phase of a multi-GPU fit: 3K+2 floats over NVLink right behind the
+    kernel) before the closed form is applied redundantly on every rank.  The reported error is the objective at
+    ``m*`` evaluated from the residuals (``stacb_m_residual``): the same number as the reference's expanded form
+    ``z2 - 2 sum(m* s) + T sum(m*^2)`` without its float32 cancellation.
     """
     eng = mjx_model.engine
     kp, qt = eng.f32(keypoints), eng.f32(q)
-    T = int(kp.shape[0])
-    s, z2 = eng.m_stats(kp, qt)
+    K = eng.K
+    buf = eng.m_stats_buffer(kp, qt)
+    T = float(kp.shape[0])
     if reduce_fn is not None:
-        s, z2, T = reduce_fn(s, z2, T)
-    d = eng.f32(is_regularized, (eng.K, 3))
-    m0 = eng.f32(initial_offsets, (eng.K, 3))
+        buf = reduce_fn(buf)
+        T = float(round(float(buf[3 * K + 1])))  # total frames over all ranks
+    s = buf[: 3 * K].reshape(K, 3)
+    d = eng.f32(is_regularized, (K, 3))
+    m0 = eng.f32(initial_offsets, (K, 3))
     reg = float(reg_coef)
-    denom = float(T) + reg * d
-    numer = s + reg * d * m0
-    m_star = numer / denom
-    data_term = z2[0] - 2.0 * torch.sum(m_star * s) + float(T) * torch.sum(m_star**2)
+    m_star = (s + reg * d * m0) / (T + reg * d)
+    data_term = eng.m_residual(kp, qt, m_star)
+    if reduce_fn is not None:
+        data_term = reduce_fn(data_term)
     reg_term = reg * torch.sum((d * (m_star - m0)) ** 2)
-    return MOptResult(params=m_star, error=data_term + reg_term)
+    return MOptResult(params=m_star, error=data_term[0] + reg_term)
 
 
 class StacCore:

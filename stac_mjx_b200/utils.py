@@ -56,8 +56,8 @@ def set_site_pos(model, offsets, site_idxs=None):
     return model.replace(site_pos=offsets)
 
 
-def handle_edge_effects(ik_only_data, n_frames_per_clip: int):
-    """Sigmoid cross-fade of overlapping clip boundaries (reference ``utils.py:393-461``)."""
+def edge_crossfade_host(data, n_frames_per_clip: int):
+    """One packed array through the reference's cross-fade (``utils.py:436-453``), on the host."""
     ov = CONTINUOUS_BATCH_OVERLAP
 
     def crossfade(a, b, center=0.5, steepness=10.0):
@@ -67,16 +67,19 @@ def handle_edge_effects(ik_only_data, n_frames_per_clip: int):
         m = m.reshape((n,) + (1,) * (a.ndim - 1))
         return (1.0 - m) * a + m * b
 
-    def f(data):
-        data = np.array(data)
-        b = data.reshape((-1, n_frames_per_clip + ov) + data.shape[1:])
-        for i in range(b.shape[0] - 1):
-            b[i, -ov:] = crossfade(b[i, -ov:], b[i + 1, :ov])
-        first, middle, last = b[0], b[1:-1, ov:], b[-1, ov:-ov]
-        return np.concatenate([first, middle.reshape((-1,) + middle.shape[2:]), last], axis=0)
+    data = np.array(data)
+    b = data.reshape((-1, n_frames_per_clip + ov) + data.shape[1:])
+    for i in range(b.shape[0] - 1):
+        b[i, -ov:] = crossfade(b[i, -ov:], b[i + 1, :ov])
+    first, middle, last = b[0], b[1:-1, ov:], b[-1, ov:-ov]
+    return np.concatenate([first, middle.reshape((-1,) + middle.shape[2:]), last], axis=0)
 
+
+def handle_edge_effects(ik_only_data, n_frames_per_clip: int):
+    """Sigmoid cross-fade of overlapping clip boundaries (reference ``utils.py:393-461``), host version: same signature and
+    semantics as the reference; ``Stac.ik_only(..., edge_effects=True)`` does the same on the GPU before the results leave it."""
     for k in ("qpos", "kp_data", "xpos", "xquat", "marker_sites"):
-        setattr(ik_only_data, k, f(getattr(ik_only_data, k)))
+        setattr(ik_only_data, k, edge_crossfade_host(getattr(ik_only_data, k), n_frames_per_clip))
     return ik_only_data
 
 

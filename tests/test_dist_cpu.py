@@ -28,17 +28,40 @@ def _worker(rank, ws, port, tmp):
 
     c = get_case("rodent")
     g = np.load(ROOT / "tests" / "golden" / "rodent.npz")
-    o = c.oracle(np.float32, 1)  # stands in for the GPU statistics kernel on this CPU-only box
+    o = c.oracle(np.float32, 1)  # stands in for the GPU statistics kernels on this CPU-only box
     kp = g["kp"][:8]
     q = g["c32_clip_qpos"].reshape(-1, c.tree.nq)[:8]
-    # m-phase: frames sharded, 3K+2 numbers all-reduced, closed form applied redundantly on every rank
+
+    class OracleEngine:
+        """CPU stand-in with the Engine methods `stac_core._m_opt` uses."""
+
+        K = c.K
+
+        def f32(self, a, shape=None):
+            return torch.as_tensor(np.asarray(a, dtype=np.float32))
+
+        def m_stats_buffer(self, kp_, q_):
+            s_, z2_ = o.m_stats(kp_.numpy(), q_.numpy())
+            return torch.tensor(np.concatenate([s_.reshape(-1), [z2_], [float(len(kp_))]]).astype(np.float32))
+
+        def m_residual(self, kp_, q_, m_):
+            return torch.tensor([o.m_residual(kp_.numpy(), q_.numpy(), m_.numpy())], dtype=torch.float32)
+
+    from stac_mjx_b200 import stac_core
+
+    mdl = stac_core.StacModel(engine=OracleEngine(), site_pos=torch.zeros(c.K, 3))
+    reg = c.setup.is_regularized
+    # m-phase: frames sharded, the 3K+2 statistics all-reduced in place, closed form applied redundantly on every rank,
+    # then the 1-float residual all-reduced
     lo, hi = parallel.shard_range(len(kp), rank, ws)
-    s, z2 = o.m_stats(kp[lo:hi], q[lo:hi])
-    s_all, z2_all, T = parallel.allreduce_m_stats(torch.tensor(s), torch.tensor([z2]), hi - lo)
-    s_ref, z2_ref = o.m_stats(kp, q)
-    assert T == len(kp)
-    np.testing.assert_allclose(s_all.numpy(), s_ref, rtol=2e-6, atol=1e-7)
-    np.testing.assert_allclose(z2_all.numpy()[0], z2_ref, rtol=2e-6)
+    res = stac_core._m_opt(mdl, None, kp[lo:hi], q[lo:hi], c.setup.initial_offsets, reg, 1.0, reduce_fn=parallel.allreduce_m_stats)
+    ref = stac_core._m_opt(mdl, None, kp, q, c.setup.initial_offsets, reg, 1.0)
+    np.testing.assert_allclose(res.params.numpy(), ref.params.numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(float(res.error), float(ref.error), rtol=1e-5)
+    mo, eo = o.m_opt(kp, q, c.setup.initial_offsets, reg, 1.0)  # the reference's expanded closed form
+    np.testing.assert_allclose(ref.params.numpy(), mo, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(float(ref.error), float(eo), rtol=2e-3)
+    s_all, z2_all = res.params, res.error.reshape(1)
     # q-phase: clips block-partitioned, no collective on the data path; results gathered clip-major
     C = 5
     clips = torch.arange(C * 3, dtype=torch.float32).reshape(C, 3)

@@ -165,3 +165,60 @@ def test_run_stac_pipeline_end_to_end(rodent, monkeypatch, tmp_path):
     st = make_stac(rodent, F + 10)
     ref = st.ik_only(np.concatenate([kp[: F + 10]]), fit.offsets)
     np.testing.assert_array_equal(ik.qpos[:F], ref.qpos[:F])
+    # the device epilogues against the host restatements of the reference (utils.py:302-347,393-461) on the same raw IK output
+    from stac_mjx_b200 import utils
+
+    st2 = make_stac(rodent, F)
+    st2.cfg.stac.continuous = True
+    raw = st2.ik_only(kp, fit.offsets)
+    assert raw.qpos.shape == (C * (F + 10), rodent.tree.nq)
+    host = utils.handle_edge_effects(raw, F)
+    for k in ("qpos", "xpos", "xquat", "marker_sites", "kp_data"):
+        np.testing.assert_array_equal(getattr(ik, k), getattr(host, k), err_msg=k)
+    dt = float(rodent.tree.timestep)
+    qv = np.concatenate([utils.compute_velocity_from_kinematics(c, dt, freejoint=True) for c in host.qpos.reshape(C, F, -1)])
+    np.testing.assert_allclose(ik.qvel, qv, rtol=2e-4, atol=2e-3)
+
+
+def test_device_epilogues_match_the_host_restatements(rodent, engine_of):
+    """stacb_edge_crossfade bit for bit against the numpy cross-fade (float64 blend rounded to float32), including the
+    reference's single-clip quirk (the clip appears twice); stacb_qvel against the host finite differences, with and without
+    a free joint (reference tests/unit/test_utils_math.py:30-40)."""
+    import torch
+
+    from stac_mjx_b200 import utils
+
+    eng = engine_of(rodent)
+    rng = np.random.default_rng(5)
+    for C, F, tail in ((1, 12, (7,)), (2, 10, (5, 3)), (5, 25, (4,)), (9, 250, (67, 4))):
+        x = rng.normal(size=(C * (F + 10),) + tail).astype(np.float32)
+        got = eng.edge_crossfade(torch.tensor(x), F, 10).cpu().numpy()
+        want = utils.edge_crossfade_host(x, F)
+        assert got.shape == want.shape
+        np.testing.assert_array_equal(got, want)
+    # velocities: free joint with unit quaternions that rotate smoothly, joints that exceed the clip limit
+    C, F, nq = 3, 40, rodent.tree.nq
+    q = rng.normal(scale=0.05, size=(C, F, nq)).cumsum(axis=1).astype(np.float32)
+    quat = rng.normal(size=(C, 1, 4)) + 0.05 * rng.normal(size=(C, F, 4)).cumsum(axis=1)
+    q[..., 3:7] = (quat / np.linalg.norm(quat, axis=-1, keepdims=True)).astype(np.float32)
+    q[1, 5:8] = q[1, 4]  # identical consecutive frames: zero angular velocity branch
+    dt = 0.002
+    got = eng.qvel(torch.tensor(q.reshape(C * F, nq)), F, dt, freejoint=True).cpu().numpy().reshape(C, F, nq - 1)
+    for c in range(C):
+        want = utils.compute_velocity_from_kinematics(q[c], dt, freejoint=True)
+        np.testing.assert_allclose(got[c, :, :3], want[:, :3], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(got[c, :, 6:], want[:, 6:], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(got[c, :, 3:6], want[:, 3:6], rtol=2e-3, atol=0.2)  # gyro: arccos near 1 amplifies float32 rounding
+        assert (got[c, -1] == 0).all() and np.abs(got[c, :, 6:]).max() <= 20.0
+    assert (got[1, 5:7, 3:6] == 0).all()
+    qs = np.array([[0.0, 0.0, 0.0], [1.0, 2.0, 3.0], [2.0, 4.0, 6.0]], dtype=np.float32)  # the reference's own no-freejoint case
+    got = eng.qvel(torch.tensor(qs), 3, 1.0, freejoint=False, max_qvel=100.0).cpu().numpy()
+    assert got.shape == (3, 3)
+    np.testing.assert_allclose(got, [[1.0, 2.0, 3.0], [1.0, 2.0, 3.0], [0.0, 0.0, 0.0]])
+    # quat_to_axisangle case of the reference (test_utils_math.py:20-27): a rotation by `angle` about x between two frames
+    angle = 0.3
+    q2 = np.zeros((2, 8), np.float32)
+    q2[:, 3] = 1.0
+    q2[1, 3:7] = [np.cos(angle / 2), np.sin(angle / 2), 0.0, 0.0]
+    got = eng.qvel(torch.tensor(q2), 2, 1.0, freejoint=True).cpu().numpy()
+    np.testing.assert_allclose(got[0, 3:6], [angle, 0.0, 0.0], atol=1e-6)
