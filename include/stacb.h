@@ -118,6 +118,18 @@ int stacb_pose_clips(const stacb_tree *tree, const float *kp, float *qpos_io, co
                      float *xquat, float *sites, float *err, int32_t *iters, int32_t *ls_evals, int32_t *root_stats,
                      int32_t *status, int C, int F, void *stream);
 
+/* The same launch on clips that OVERLAP in memory: clip c starts `clip_stride` frames after clip c-1 in one session buffer
+ *   kp [(C-1)*clip_stride + F, 3K]
+ * so the 10-frame look-ahead of the reference's `continuous` batching (utils.batch_kp_data, stac_mjx/utils.py:350-389: windows
+ * of n_frames_per_clip + 10 frames every n_frames_per_clip frames) is read in place by the kernel instead of being
+ * materialised per clip on the host (clip_stride = n_frames_per_clip, F = n_frames_per_clip + 10; the caller appends the
+ * reference's 10 wrap-padded frames after the last clip).  clip_stride = F is stacb_pose_clips. */
+int stacb_pose_session(const stacb_tree *tree, const float *kp, int clip_stride, float *qpos_io, const float *site_pos,
+                       const float *lb, const float *ub, const uint8_t *part_masks, int P, int do_root, int root_kp_idx,
+                       const uint8_t *trunk_kps, int root_dims, float tol, int maxiter, int maxls, float *qpos, float *xpos,
+                       float *xquat, float *sites, float *err, int32_t *iters, int32_t *ls_evals, int32_t *root_stats,
+                       int32_t *status, int C, int F, void *stream);
+
 /* _m_opt sufficient statistics over T frames (stac_core.py:146-159):
  *   s[k,i] = sum_t sum_j R_tk[j,i] (y_tk[j] - p_tk[j]),   z2 = sum_t sum_k |y_tk - p_tk|^2.
  *   kp [T,3K]  q [T,nq]  scratch [stacb_m_scratch_floats(tree, T)]

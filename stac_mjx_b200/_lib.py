@@ -16,6 +16,7 @@ SYMBOLS = (
     "stacb_loss_grad",
     "stacb_q_opt",
     "stacb_pose_clips",
+    "stacb_pose_session",
     "stacb_m_stats",
     "stacb_m_residual",
     "stacb_m_scratch_floats",
@@ -80,6 +81,9 @@ def lib() -> C.CDLL:
         L.stacb_q_opt.argtypes = [vp] * 8 + [f32, i32, i32] + [vp] * 4 + [i32, vp]
         L.stacb_pose_clips.argtypes = (
             [vp] * 7 + [i32, i32, i32, vp, i32, f32, i32, i32] + [vp] * 9 + [i32, i32, vp]
+        )
+        L.stacb_pose_session.argtypes = (
+            [vp, vp, i32] + [vp] * 5 + [i32, i32, i32, vp, i32, f32, i32, i32] + [vp] * 9 + [i32, i32, vp]
         )
         L.stacb_m_stats.argtypes = [vp] * 5 + [i32, vp]
         L.stacb_m_residual.argtypes = [vp] * 6 + [i32, vp]

@@ -292,7 +292,9 @@ static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
   {
     // register-resident solver: latency mode (2 * NC warps per chain) for few chains, throughput mode (one warp per chain)
     // for many, dense throughput mode (registers capped for 16 warps per SM) from 16 chains per SM
-    int sched = (a.C <= 2 * sms) ? 1 : (a.C >= 16 * sms ? 2 : 0);
+    // measured on B200 (profiles/mode_sweep_r2a.txt): latency mode wins while two CTAs per SM hold every chain, one warp per chain
+    // while 8 warps per SM do, the dense variant (16 warps per SM) beyond that
+    int sched = (a.C <= 2 * sms) ? 1 : (a.C > 8 * sms ? 2 : 0);
     if (g_force_mode >= 0) sched = g_force_mode;
     const int nc = sched == 1 ? 2 : (sched == 3 ? 3 : 0);
     const size_t area = ((size_t)2 * t->T.nqp + 7 * (size_t)t->T.pqn) * 4;
@@ -376,11 +378,12 @@ extern "C" int stacb_q_opt(const stacb_tree *t, const float *q0, const float *kp
   return run_batch(t, a, (cudaStream_t)stream);
 }
 
-extern "C" int stacb_pose_clips(const stacb_tree *t, const float *kp, float *qpos_io, const float *site_pos, const float *lb, const float *ub,
-                                const uint8_t *part_masks, int P, int do_root, int root_kp_idx, const uint8_t *trunk_kps, int root_dims,
-                                float tol, int maxiter, int maxls, float *qpos, float *xpos, float *xquat, float *sites, float *err,
-                                int32_t *iters, int32_t *ls_evals, int32_t *root_stats, int32_t *status, int C, int F, void *stream) {
-  if (!t || !kp || !qpos_io || !site_pos || !lb || !ub || C < 0 || F < 0 || P < 0) return fail(STACB_E_INVALID, "stacb_pose_clips: bad argument");
+extern "C" int stacb_pose_session(const stacb_tree *t, const float *kp, int clip_stride, float *qpos_io, const float *site_pos, const float *lb,
+                                  const float *ub, const uint8_t *part_masks, int P, int do_root, int root_kp_idx, const uint8_t *trunk_kps,
+                                  int root_dims, float tol, int maxiter, int maxls, float *qpos, float *xpos, float *xquat, float *sites,
+                                  float *err, int32_t *iters, int32_t *ls_evals, int32_t *root_stats, int32_t *status, int C, int F, void *stream) {
+  if (!t || !kp || !qpos_io || !site_pos || !lb || !ub || C < 0 || F < 0 || P < 0 || clip_stride < 0)
+    return fail(STACB_E_INVALID, "stacb_pose_clips: bad argument");
   if (P > 0 && !part_masks) return fail(STACB_E_INVALID, "stacb_pose_clips: part_masks is null");
   if (do_root && (root_kp_idx < 0 || root_kp_idx >= t->T.K || F < 1)) return fail(STACB_E_INVALID, "stacb_pose_clips: bad root keypoint");
   if ((iters == nullptr) != (ls_evals == nullptr)) return fail(STACB_E_INVALID, "stacb_pose_clips: iters and ls_evals go together");
@@ -390,7 +393,16 @@ extern "C" int stacb_pose_clips(const stacb_tree *t, const float *kp, float *qpo
   a.root_kp_idx = root_kp_idx; a.trunk_kps = trunk_kps; a.root_dims = root_dims; a.tol = tol; a.maxiter = maxiter; a.maxls = maxls;
   a.qpos = qpos; a.xpos = xpos; a.xquat = xquat; a.sites = sites; a.err = err; a.iters = iters; a.ls_evals = ls_evals;
   a.root_stats = root_stats; a.status = status; a.C = C; a.F = F; a.counter = t->counter;
+  a.kp_stride = (long long)clip_stride * 3 * t->T.K;
   return run_pose(t, a, (cudaStream_t)stream);
+}
+
+extern "C" int stacb_pose_clips(const stacb_tree *t, const float *kp, float *qpos_io, const float *site_pos, const float *lb, const float *ub,
+                                const uint8_t *part_masks, int P, int do_root, int root_kp_idx, const uint8_t *trunk_kps, int root_dims,
+                                float tol, int maxiter, int maxls, float *qpos, float *xpos, float *xquat, float *sites, float *err,
+                                int32_t *iters, int32_t *ls_evals, int32_t *root_stats, int32_t *status, int C, int F, void *stream) {
+  return stacb_pose_session(t, kp, F, qpos_io, site_pos, lb, ub, part_masks, P, do_root, root_kp_idx, trunk_kps, root_dims, tol, maxiter, maxls,
+                            qpos, xpos, xquat, sites, err, iters, ls_evals, root_stats, status, C, F, stream);
 }
 
 static int run_mphase(const stacb_tree *t, MArgs a, cudaStream_t s) {
@@ -440,7 +452,7 @@ extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, vo
 }
 
 extern "C" int stacb_tree_set_mode(stacb_tree *t, int mode) {
-  if (!t || mode < -1 || mode > 3)
+  if (!t || mode < -1 || mode > 6)
     return fail(STACB_E_INVALID, "stacb_tree_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency), 2 (dense throughput) or 3 (wide latency)");
   t->mode.store(mode);
   return STACB_OK;

@@ -968,6 +968,7 @@ struct PoseArgs {
   int do_root, root_kp_idx; const uint8_t *trunk_kps; int root_dims; float tol; int maxiter, maxls;
   float *qpos, *xpos, *xquat, *sites, *err; int32_t *iters, *ls_evals, *root_stats, *status; int C, F;
   int *counter;
+  long long kp_stride;  // floats between the first frames of consecutive clips (F * 3K for packed clips; less when clips overlap)
 };
 
 // MODE 0: throughput (one warp per chain, 4 chains per CTA); MODE 1: latency (4 cooperating warps per chain);
@@ -1028,7 +1029,7 @@ __global__ void __launch_bounds__(MODE == 3 ? 128 * GRP : 128, MODE == 2 ? 4 : 1
 #pragma unroll
     for (int m = 0; m < CPL; m++) q[m] = co.valid[m] ? a.qpos_io[(size_t)c * nq + lane + 32 * m] : 0.f;
     bool bad = false;
-    const float *kpc = a.kp + (size_t)c * a.F * 3 * K;
+    const float *kpc = a.kp + (size_t)c * a.kp_stride;
     for (int sidx = 0; sidx < n_stage; sidx++) {
       const bool is_root = sidx < n_root;
       const int f = is_root ? 0 : (sidx - n_root) / S1;   // frame

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
     float q[NS], q0[NS], x[NS];
     slots_gather<JM>(co, sa, ch.qbuf, q);
     bool bad = false;
-    const float *kpc = a.kp + (size_t)c * a.F * 3 * K;
+    const float *kpc = a.kp + (size_t)c * a.kp_stride;
     for (int sidx = 0; sidx < n_stage; sidx++) {
       const bool is_root = sidx < n_root;
       const int f = is_root ? 0 : (sidx - n_root) / S1;   // frame

@@ -24,6 +24,8 @@ cudaError_t FN(launch_fast_pose_, V_FJM, V_FRT, V_FNBF)(const DevTree &T, const 
     case 1: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 2, 1>, T, a, grid, block, smem, s);
     case 3: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 3, 1>, T, a, grid, block, smem, s);
     case 2: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 4>, T, a, grid, block, smem, s);
+    case 5: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 3>, T, a, grid, block, smem, s);
+    case 6: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 2>, T, a, grid, block, smem, s);
     default: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 1>, T, a, grid, block, smem, s);
   }
 }

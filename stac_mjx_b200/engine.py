@@ -130,11 +130,22 @@ class Engine:
 
     # -- fused root_optimization + pose_optimization over clips -------------
     def pose_clips(self, kp, qpos_io, site_pos, lb, ub, part_masks, *, do_root, root_kp_idx=-1, trunk_kps=None,
-                   root_dims=7, tol=1e-4, maxiter=400, maxls=15, out=None, want_stats=True):  # fmt: skip
-        """kp [C,F,3K] (device), qpos_io [C,nq] (device, updated in place). Returns dict of device tensors."""
+                   root_dims=7, tol=1e-4, maxiter=400, maxls=15, out=None, want_stats=True, session=None):  # fmt: skip
+        """kp [C,F,3K] (device), qpos_io [C,nq] (device, updated in place). Returns dict of device tensors.
+
+        ``session=(C, F, clip_stride)``: `kp` is ONE session buffer [(C-1)*clip_stride + F, 3K] whose clips overlap in memory
+        (the `continuous` look-ahead read in place by the kernel, `stacb_pose_session`)."""
         kp = self.f32(kp)
-        Cn, F = int(kp.shape[0]), int(kp.shape[1])
-        if kp.shape[2] != 3 * self.K:
+        if session is not None:
+            Cn, F, stride = (int(v) for v in session)
+            if kp.dim() != 2 or kp.shape[1] != 3 * self.K or (Cn > 0 and kp.shape[0] < (Cn - 1) * stride + F):
+                raise ValueError("session kp must be [(C-1)*clip_stride + F, 3K]")
+        else:
+            if kp.dim() != 3:
+                raise ValueError("kp must be [C, F, 3K]")
+            Cn, F = int(kp.shape[0]), int(kp.shape[1])
+            stride = F
+        if kp.shape[-1] != 3 * self.K:
             raise ValueError("kp must be [C, F, 3K]")
         if not (isinstance(qpos_io, torch.Tensor) and qpos_io.is_cuda and qpos_io.dtype == torch.float32 and qpos_io.is_contiguous()):
             raise ValueError("qpos_io must be a contiguous float32 CUDA tensor [C, nq] (it is updated in place)")
@@ -157,13 +168,13 @@ class Engine:
         status = o("status", Cn, dtype=torch.int32)
         if Cn == 0 or F == 0:
             return out
-        rc = self._L.stacb_pose_clips(
-            self._h, _ptr(kp), _ptr(qpos_io), _ptr(site_pos), _ptr(lb), _ptr(ub), _ptr(pm) if P else None, P,
+        rc = self._L.stacb_pose_session(
+            self._h, _ptr(kp), stride, _ptr(qpos_io), _ptr(site_pos), _ptr(lb), _ptr(ub), _ptr(pm) if P else None, P,
             int(do_root), int(root_kp_idx), _ptr(trunk), int(root_dims), float(tol), int(maxiter), int(maxls),
             _ptr(qpos), _ptr(xpos), _ptr(xquat), _ptr(sites), _ptr(err), _ptr(iters), _ptr(ls), _ptr(rs), _ptr(status),
             Cn, F, self._stream(),
         )  # fmt: skip
-        _lib.check(rc, "stacb_pose_clips")
+        _lib.check(rc, "stacb_pose_session")
         return out
 
     # -- stac_core._m_opt sufficient statistics ------------------------------

@@ -52,6 +52,8 @@ def save_data_to_h5(config, kp_names, names_qpos, names_xpos, kp_data, marker_si
         f.create_dataset("kp_names", data=np.array(kp_names, dtype="S"))
         f.create_dataset("names_qpos", data=np.array(names_qpos, dtype="S"))
         f.create_dataset("names_xpos", data=np.array(names_xpos, dtype="S"))
+        # the arrays may be views of page-locked result buffers (Stac.ik_only hands them out without a second host copy):
+        # h5py reads them in place
         for name, arr in (("kp_data", kp_data), ("marker_sites", marker_sites), ("offsets", offsets), ("qpos", qpos),
                           ("qvel", qvel), ("xpos", xpos), ("xquat", xquat)):  # fmt: skip
             f.create_dataset(name, data=arr, compression="gzip")

@@ -192,16 +192,29 @@ class Stac:
         _nvtx = torch.cuda.nvtx
         _nvtx.range_push("stac.ik_only/h2d")
         kp_data = np.asarray(kp_data, dtype=np.float32)
-        batched_kp_data = utils.batch_kp_data(kp_data, self.cfg.stac.n_frames_per_clip, continuous=self.cfg.stac.continuous)
         eng = self._engine
-        C, F = batched_kp_data.shape[:2]
+        Fc = int(self.cfg.stac.n_frames_per_clip)
+        continuous = bool(self.cfg.stac.continuous)
+        ov = utils.CONTINUOUS_BATCH_OVERLAP if continuous else 0
+        C, F = int(kp_data.shape[0] // Fc), Fc + ov
+        if C < 1 or (continuous and kp_data.shape[0] < F):
+            raise ValueError("not enough frames for one clip")
         rank, ws = parallel.world()
         lo, hi = parallel.shard_range(C, rank, ws)
         offsets = np.asarray(offsets, dtype=np.float32)
         site_pos = eng.f32(offsets, (eng.K, 3))
-        # pinned staging -> device: the step's H2D copy
-        stage = self._pinned("kp_in", (hi - lo, F, batched_kp_data.shape[2]), torch.float32)
-        stage.copy_(torch.from_numpy(np.ascontiguousarray(batched_kp_data[lo:hi])))
+        # Keypoint ingest: this rank's frames go straight from the session array into ONE page-locked staging buffer -- clips are
+        # windows of F frames every Fc frames of it (utils.batch_kp_data, reference utils.py:350-389), read in place by the kernel,
+        # so the `continuous` look-ahead is neither materialised per clip on the host nor copied twice.  The reference wrap-pads
+        # the LAST clip with its own first frames (utils.py:377-381): appended behind the session on the rank that owns it.
+        n_rows = max(hi - lo - 1, 0) * Fc + F if hi > lo else 0
+        stage = self._pinned("kp_in", (n_rows, kp_data.shape[1]), torch.float32)
+        if hi > lo:
+            src = kp_data[lo * Fc : min(lo * Fc + n_rows, C * Fc)]
+            stage[: len(src)].copy_(torch.from_numpy(src))
+            if len(src) < n_rows:  # only the rank holding the last clip: its look-ahead wraps onto the clip's own start
+                last = utils.batch_kp_data(kp_data[(C - 1) * Fc :], Fc, continuous=True)[-1]
+                stage[len(src) :].copy_(torch.from_numpy(np.ascontiguousarray(last[Fc : Fc + n_rows - len(src)])))
         kp_dev = stage.to(eng.device, non_blocking=True)
         qio = eng.f32(self._mj_model.qpos0).repeat(hi - lo, 1).contiguous()
         has_root = self._root_kp_idx != -1 and not self._fixed
@@ -215,7 +228,7 @@ class Stac:
         out = eng.pose_clips(
             kp_dev, qio, site_pos, self._lb, self._ub, self._indiv_parts, do_root=1 if has_root else 0,
             root_kp_idx=max(self._root_kp_idx, 0), trunk_kps=self._trunk_kps, root_dims=4 if self._slidejoint else 7,
-            tol=q.tol, maxiter=q.maxiter, maxls=q.maxls,
+            tol=q.tol, maxiter=q.maxiter, maxls=q.maxls, session=(hi - lo, F, Fc),
         )  # fmt: skip
         _nvtx.range_pop()
         self.last_stats = {"iters": out["iters"], "ls_evals": out["ls_evals"], "status": out["status"], "root_stats": out["root_stats"]}
@@ -230,7 +243,10 @@ class Stac:
             "marker_sites": res["sites"].transpose(0, 1).reshape(C * F, K, 3),  # frame-major interleave (stac.py:486)
             "err": res["err"],
         }
-        kp_packed = batched_kp_data.reshape(-1, batched_kp_data.shape[-1])
+        # StacData.kp_data: the reference returns the batched keypoints flattened (stac.py:498-500); after the cross-fade of identical
+        # look-ahead copies that is the session itself up to the blend's rounding, so it is produced on the host from the input
+        kp_packed = utils.batch_kp_data(kp_data, Fc, continuous=continuous)
+        kp_packed = kp_packed.reshape(-1, kp_packed.shape[-1])
         if edge_effects:  # device epilogue: sigmoid cross-fade of the look-ahead overlap, overlaps removed (utils.py:393-461)
             if not self.cfg.stac.continuous:
                 raise ValueError("edge_effects needs cfg.stac.continuous clips (the overlap is what is cross-faded)")

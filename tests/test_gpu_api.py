@@ -222,3 +222,34 @@ def test_device_epilogues_match_the_host_restatements(rodent, engine_of):
     q2[1, 3:7] = [np.cos(angle / 2), np.sin(angle / 2), 0.0, 0.0]
     got = eng.qvel(torch.tensor(q2), 2, 1.0, freejoint=True).cpu().numpy()
     np.testing.assert_allclose(got[0, 3:6], [angle, 0.0, 0.0], atol=1e-6)
+
+
+def test_continuous_look_ahead_is_read_in_place(rodent):
+    """`continuous` clips (windows of F + 10 frames every F frames, reference utils.py:350-389): Stac.ik_only stages the session
+    once and the kernel reads the overlapping windows in place (stacb_pose_session); the result equals the launch on the
+    materialised per-clip copies bit for bit, including the last clip's wrap-padding."""
+    import torch
+
+    from stac_mjx_b200 import utils
+
+    F, C = 12, 4
+    st = make_stac(rodent, F)
+    st.cfg.stac.continuous = True
+    kp, _, _ = rodent.session(C * F, F, seed=31)
+    d = st.ik_only(kp, rodent.setup.initial_offsets)
+    clips = utils.batch_kp_data(kp, F, continuous=True)
+    assert clips.shape == (C, F + 10, 3 * rodent.K)
+    eng, s = st._engine, rodent.setup
+    qio = torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (C, 1)), device=eng.device)
+    out = eng.pose_clips(clips, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())
+    np.testing.assert_array_equal(d.qpos, out["qpos"].cpu().numpy().reshape(C * (F + 10), -1))
+    np.testing.assert_array_equal(d.xpos, out["xpos"].cpu().numpy().reshape(C * (F + 10), -1, 3))
+    np.testing.assert_array_equal(d.kp_data, clips.reshape(C * (F + 10), -1))
+    # a second call reuses the page-locked result buffers only once the first result has been released
+    d2 = st.ik_only(kp, rodent.setup.initial_offsets)
+    assert d2.qpos is not d.qpos and not np.shares_memory(d2.qpos, d.qpos)
+    np.testing.assert_array_equal(d2.qpos, d.qpos)
+    ptr = d2.qpos.ctypes.data
+    del d2
+    d3 = st.ik_only(kp, rodent.setup.initial_offsets)
+    assert d3.qpos.ctypes.data == ptr  # released -> reused, no second host copy either way

@@ -281,3 +281,91 @@ def test_make_qs_accepts_torch_and_numpy_in_any_mix():
         for a, b in ((torch.from_numpy(q0), torch.from_numpy(q)), (q0, torch.from_numpy(q)), (torch.from_numpy(q0), q)):
             out = utils.make_qs(a, mm, b)
             assert isinstance(out, torch.Tensor) and np.array_equal(out.numpy(), want)
+
+
+class _FakeH5Dataset:
+    def __init__(self, data, compression):
+        self.data, self.compression = np.asarray(data), compression
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def __iter__(self):
+        return iter(self.data)
+
+
+class _FakeH5File(dict):
+    """The slice of the h5py.File API the writer / reader use, backed by a dict that outlives the `with` block."""
+
+    stores: dict = {}
+
+    def __init__(self, path, mode):
+        super().__init__()
+        self.path, self.mode = str(path), mode
+        if mode == "r":
+            self.update(self.stores[self.path])
+
+    def create_dataset(self, name, data=None, compression=None):
+        assert self.mode == "w" and name not in self
+        self[name] = _FakeH5Dataset(data, compression)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.mode == "w":
+            self.stores[self.path] = dict(self)
+        return False
+
+
+def test_h5_writer_and_reader_run_for_real_against_the_reference_layout(monkeypatch, tmp_path):
+    """`io.save_data_to_h5` / `io.load_stac_data` (reference io.py:194-278) executed end to end.  h5py is absent from this
+    image, so an in-memory stand-in with the h5py.File surface the two functions touch is injected: the test pins the dataset
+    names and order, the string / bytes encodings, which datasets are gzip-compressed, and the round trip -- with the real
+    h5py the same body runs below when it is installed."""
+    import sys
+    import types
+
+    from stac_mjx_b200 import io
+    from stac_mjx_b200.model import load_fixture
+
+    _, cfg = load_fixture("rodent")
+    rng = np.random.default_rng(0)
+    d = io.StacData(
+        qpos=rng.normal(size=(6, 74)).astype(np.float32), xpos=rng.normal(size=(6, 67, 3)).astype(np.float32),
+        xquat=rng.normal(size=(6, 67, 4)).astype(np.float32), marker_sites=rng.normal(size=(6, 23, 3)).astype(np.float32),
+        offsets=rng.normal(size=(23, 3)).astype(np.float32), kp_data=rng.normal(size=(6, 69)).astype(np.float32),
+        names_qpos=[f"q{i}" for i in range(74)], names_xpos=[f"b{i}" for i in range(67)], kp_names=[f"k{i}" for i in range(23)],
+        qvel=rng.normal(size=(6, 73)).astype(np.float32),
+    )  # fmt: skip
+
+    def roundtrip(path):
+        io.save_data_to_h5(config=cfg, file_path=path, **d.as_dict())
+        cfg2, d2 = io.load_stac_data(path)
+        assert cfg2.to_dict() == cfg.to_dict()
+        for k in ("qpos", "xpos", "xquat", "marker_sites", "offsets", "kp_data", "qvel"):
+            np.testing.assert_array_equal(getattr(d2, k), getattr(d, k))
+        assert d2.names_qpos == d.names_qpos and d2.names_xpos == d.names_xpos and d2.kp_names == d.kp_names
+
+    fake = types.ModuleType("h5py")
+    fake.File = _FakeH5File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    path = tmp_path / "fit.h5"
+    roundtrip(path)
+    store = _FakeH5File.stores[str(path)]
+    # the reference's datasets, in its order (io.py:225-237)
+    assert list(store) == ["config", "kp_names", "names_qpos", "names_xpos", "kp_data", "marker_sites", "offsets", "qpos", "qvel", "xpos", "xquat"]
+    assert store["config"].data.dtype.kind == "S" and store["config"].data.shape == () and store["config"].compression is None
+    for k in ("kp_names", "names_qpos", "names_xpos"):
+        assert store[k].data.dtype.kind == "S" and store[k].compression is None
+    for k in ("kp_data", "marker_sites", "offsets", "qpos", "qvel", "xpos", "xquat"):
+        assert store[k].compression == "gzip" and store[k].data.dtype == np.float32
+    import yaml
+
+    assert yaml.safe_load(store["config"].data[()].decode("utf-8"))["model"]["N_ITER_Q"] == cfg.model.N_ITER_Q
+    monkeypatch.delitem(sys.modules, "h5py")
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        return
+    roundtrip(tmp_path / "real.h5")
