@@ -213,7 +213,9 @@ class Stac:
             src = kp_data[lo * Fc : min(lo * Fc + n_rows, C * Fc)]
             stage[: len(src)].copy_(torch.from_numpy(src))
             if len(src) < n_rows:  # only the rank holding the last clip: its look-ahead wraps onto the clip's own start
-                last = utils.batch_kp_data(kp_data[(C - 1) * Fc :], Fc, continuous=True)[-1]
+                last = np.pad(kp_data[(C - 1) * Fc : (C - 1) * Fc + F], ((0, ov), (0, 0)), mode="wrap")
+                if len(last) != F:  # left-over frames behind the last clip: the reference's np.stack of unequal windows fails too
+                    raise ValueError("all input arrays must have the same shape (session length is not a multiple of n_frames_per_clip)")
                 stage[len(src) :].copy_(torch.from_numpy(np.ascontiguousarray(last[Fc : Fc + n_rows - len(src)])))
         kp_dev = stage.to(eng.device, non_blocking=True)
         qio = eng.f32(self._mj_model.qpos0).repeat(hi - lo, 1).contiguous()
