@@ -167,7 +167,9 @@ int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream)
  * 1 latency mode (four cooperating warps per chain, speculative line search), 2 dense throughput mode (registers capped so 16
  * chains fit per SM; chosen automatically from 16 chains per SM), 3 wide latency mode (register-resident path: six warps per
  * chain speculating on three line-search candidates; general path: each of the four speculative evaluations carried out by
- * three warps sharing the bodies of a wide tree).  Results do not depend on the mode (bit-identical).
+ * three warps sharing the bodies of a wide tree), 4 pair mode (register-resident path: two warps per chain evaluate two line-search
+ * candidates at once, then the accepted point's gradient and the next extrapolation at once; chosen automatically between one
+ * chain per SM and four).  Results do not depend on the mode (bit-identical).
  * The setting is a property of the handle, not of the process; do not change it while a launch of the same handle is being
  * enqueued from another thread. */
 int stacb_tree_set_mode(stacb_tree *tree, int mode);

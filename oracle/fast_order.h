@@ -65,6 +65,29 @@ static inline void f_sincos(REAL x, REAL *sp, REAL *cp) {
   *cp = (REAL)fmaf(r2 * r2, pc, fmaf(-0.5f, r2, 1.0f));
 }
 
+/* normalize4_nr of csrc/stacb_math.cuh: integer-seeded reciprocal square root, two Newton steps and one in residual form */
+static inline q4 f_normalize4(q4 q, REAL *rinv_out) {
+  if (!IS_F32) {
+    REAL n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    REAL r = n2 > 0 ? R(1) / (REAL)sqrt((double)n2) : R(0);
+    q4 o = { q.w * r, q.x * r, q.y * r, q.z * r };
+    *rinv_out = r;
+    return o;
+  }
+  float w = (float)q.w, x = (float)q.x, y = (float)q.y, z = (float)q.z;
+  float n2 = fmaf(z, z, fmaf(y, y, fmaf(x, x, w * w)));
+  float h = 0.5f * n2;
+  int32_t bits; memcpy(&bits, &n2, 4);
+  bits = 0x5f3759df - (bits >> 1);
+  float r; memcpy(&r, &bits, 4);
+  for (int i = 0; i < 2; i++) r = r * fmaf(-(h * r), r, 1.5f);
+  float e = fmaf(-(n2 * r), r, 1.0f);
+  r = fmaf(0.5f * r, e, r);
+  q4 o = { (REAL)(w * r), (REAL)(x * r), (REAL)(y * r), (REAL)(z * r) };
+  *rinv_out = (REAL)r;
+  return o;
+}
+
 static void fast_destroy(ofast *F) { if (F) { free(F->passive); free(F); } }
 
 /* NULL when the register-resident path does not serve the model (mirrors stacb_tree_create / fits_fast) */
@@ -151,7 +174,7 @@ static ofast *fast_create(const omodel *m, const osched *s) {
 
 typedef struct {
   v3 P[LANES]; q4 Q[LANES], Qp[LANES];
-  v3 anc[LANES][FJ], ax[LANES][FJ];
+  v3 lp[LANES][FJ]; q4 lq[LANES][FJ]; /* parent-frame pose of the body before hinge slot j >= 1 */
   v3 s[LANES], res[LANES];
   v3 fpos; q4 fq; REAL frinv;
 } ffwd;
@@ -175,7 +198,7 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
   if (F->has_free) {
     S->fpos.x = pt[0][JM]; S->fpos.y = pt[1][JM]; S->fpos.z = pt[2][JM];
     q4 raw = { pt[3][JM], pt[4][JM], pt[5][JM], pt[6][JM] };
-    S->fq = c_normalize4(raw, &S->frinv);
+    S->fq = f_normalize4(raw, &S->frinv);
   } else {
     S->fpos.x = S->fpos.y = S->fpos.z = R(0); S->fq.w = R(1); S->fq.x = S->fq.y = S->fq.z = R(0); S->frinv = R(1);
   }
@@ -191,8 +214,7 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
                r_fma(F->C[l].z, sn, r_fma(F->B[l].z, ct, F->A[l].z)) };
     if (F->pfree[l]) { pos = S->fpos; quat = S->fq; }
     for (int j = 1; j < JM; j++) {
-      S->anc[l][j] = add3(pos, f_rotq(F->jps[l][j], quat));
-      S->ax[l][j] = f_rotq(F->jax[l][j], quat);
+      S->lp[l][j] = pos; S->lq[l][j] = quat;
       ct = r_fma(ch[j], ch[j], -(sh[j] * sh[j]));
       sn = R(2) * (sh[j] * ch[j]);
       REAL om = R(1) - ct;
@@ -252,7 +274,10 @@ static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANE
     v3 T0 = sub3(Tq, c_cross(sub3(pp, c), Fo));
     v3 Fp = f_rotq(Fo, pc), Tp = f_rotq(T0, pc);
     g[l][0] = c_dot3(F->ax0[l], sub3(Tp, c_cross(F->anc0[l], Fp)));
-    for (int j = 1; j < JM; j++) g[l][j] = c_dot3(S->ax[l][j], sub3(Tp, c_cross(S->anc[l][j], Fp)));
+    for (int j = 1; j < JM; j++) {
+      v3 anc = add3(S->lp[l][j], f_rotq(F->jps[l][j], S->lq[l][j])), ax = f_rotq(F->jax[l][j], S->lq[l][j]);
+      g[l][j] = c_dot3(ax, sub3(Tp, c_cross(anc, Fp)));
+    }
     g[l][JM] = R(0);
   }
   if (free_wanted) {
@@ -315,10 +340,19 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
   fsites st; ffwd S;
   fast_sites(F, site_pos, kp, kpmask, &st);
   REAL q0s[LANES][FNS], x[LANES][FNS], y[LANES][FNS], g[LANES][FNS], xn[LANES][FNS], d[LANES][FNS], gt[LANES][FNS], pt[LANES][FNS];
-  REAL lbs[LANES][FNS], ubs[LANES][FNS];
+  REAL lbs[LANES][FNS], ubs[LANES][FNS], gm[LANES][FNS], dn[LANES][FNS];
   int bits[LANES][FNS];
   fast_gather(F, q0, q0s); fast_gather(F, lb, lbs); fast_gather(F, ub, ubs); fast_bits(F, qmask, bits);
   const int fw = fast_free_wanted(F, bits);
+  /* frozen slots (valid, not optimised): zero gradient; they stay at q0 inside the solve (unbounded effective box) and the squared
+     length of the reference's one move to clip(q0) enters the first line search through sqn (solve_setup of stacb_fast.cuh) */
+  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
+    int frozen = F->valid[l][mm] && !bits[l][mm];
+    gm[l][mm] = bits[l][mm] ? R(1) : R(0);
+    dn[l][mm] = frozen ? clipr(q0s[l][mm], lbs[l][mm], ubs[l][mm]) - q0s[l][mm] : R(0);
+    if (frozen) { lbs[l][mm] = -(REAL)INFINITY; ubs[l][mm] = (REAL)INFINITY; }
+  }
+  const REAL sqn = fast_dot(F, dn, dn);
   /* passive coordinates: squared length of the move to clip(q0), dealt out over the lanes */
   REAL sqp;
   {
@@ -333,28 +367,28 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
       }
       part[l] = acc;
     }
-    sqp = butterfly32(part);
+    sqp = sqn + butterfly32(part);
   }
   memcpy(params, q0, sizeof(REAL) * m->nq);
-  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) { x[l][mm] = F->valid[l][mm] ? q0s[l][mm] : R(0); y[l][mm] = x[l][mm]; }
+  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) { x[l][mm] = q0s[l][mm]; y[l][mm] = x[l][mm]; }
   REAL t = R(1), step = R(1), err = (REAL)INFINITY;
   solve_info info = { err, 0, 0 };
   if (maxiter <= 0) return info;
   do {
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) pt[l][mm] = bits[l][mm] ? y[l][mm] : q0s[l][mm];
+    memcpy(pt, y, sizeof(pt));
     REAL fy = fast_fwd(F, &st, pt, &S);
     fast_bwd(F, &S, fw, g);
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (!bits[l][mm]) g[l][mm] = R(0);
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) g[l][mm] = g[l][mm] * gm[l][mm];
     REAL stp = step;
     int halv = 0;
     for (;;) {
       for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
-        xn[l][mm] = F->valid[l][mm] ? clipr(r_fma(-stp, g[l][mm], y[l][mm]), lbs[l][mm], ubs[l][mm]) : R(0);
+        xn[l][mm] = clipr(r_fma(-stp, g[l][mm], y[l][mm]), lbs[l][mm], ubs[l][mm]);
         d[l][mm] = xn[l][mm] - y[l][mm];
       }
       REAL sq = fast_dot(F, d, d), dg = fast_dot(F, d, g);
       sq = sq + sqp;
-      for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) pt[l][mm] = bits[l][mm] ? xn[l][mm] : q0s[l][mm];
+      memcpy(pt, xn, sizeof(pt));
       REAL fn = fast_fwd(F, &st, pt, &S);
       info.ls_evals++;
       REAL dec = stp * (fn - fy);
@@ -362,15 +396,17 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
       if (!(dec > cond + R_EPS) || halv >= maxls) break;
       stp = stp * R(0.5); halv++;
     }
+    if (info.iters == 0) ls_trace_push(-1);
+    ls_trace_push(halv);
     /* S holds the state of the accepted candidate: gradient at x+ */
     fast_bwd(F, &S, fw, gt);
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (!bits[l][mm]) gt[l][mm] = R(0);
+    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) gt[l][mm] = gt[l][mm] * gm[l][mm];
     step = (stp <= R(1e-6)) ? R(1) : stp / R(0.5);
     REAL tn = R(0.5) * (R(1) + r_sqrt(r_fma(R(4) * t, t, R(1))));
     REAL beta = (t - R(1)) / tn;
     for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
       y[l][mm] = r_fma(beta, xn[l][mm] - x[l][mm], xn[l][mm]);
-      d[l][mm] = F->valid[l][mm] ? clipr(xn[l][mm] - gt[l][mm], lbs[l][mm], ubs[l][mm]) - xn[l][mm] : R(0);
+      d[l][mm] = clipr(xn[l][mm] - gt[l][mm], lbs[l][mm], ubs[l][mm]) - xn[l][mm];
       x[l][mm] = xn[l][mm];
     }
     err = r_sqrt(fast_dot(F, d, d));
@@ -379,6 +415,9 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
   } while (err > tol && info.iters < maxiter);
   info.error = err;
   for (int i = 0; i < F->npassive; i++) { int p = F->passive[i]; params[p] = clipr(q0[p], lb[p], ub[p]); }
-  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (F->valid[l][mm]) params[F->adr[l][mm]] = x[l][mm];
+  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (F->valid[l][mm]) {
+    int a = F->adr[l][mm];
+    params[a] = bits[l][mm] ? x[l][mm] : clipr(x[l][mm], lb[a], ub[a]);  /* the reference's iterate of a frozen coordinate is clip(q0) */
+  }
   return info;
 }

@@ -591,6 +591,21 @@ typedef struct { REAL error; int iters; int ls_evals; } solve_info;
 /* diagnostic: histogram of the accepted line-search candidate index (rodent session: 17.5 % / 66.6 % / 15.6 % at 0 / 1 / 2) */
 static long long g_ls_hist[17];
 void oracle_ls_hist(long long *out, int reset) { for (int i = 0; i < 17; i++) { out[i] = g_ls_hist[i]; if (reset) g_ls_hist[i] = 0; } }
+/* diagnostic: the accepted candidate index of every iteration, in order (single-threaded runs only); -1 marks the start of a solve */
+#define LS_TRACE_MAX (1 << 22)
+static signed char *g_ls_trace; static long long g_ls_trace_n;
+static void ls_trace_push(int v) {
+  if (!g_ls_trace) return;
+  if (g_ls_trace_n < LS_TRACE_MAX) g_ls_trace[g_ls_trace_n++] = (signed char)v;
+}
+long long oracle_ls_trace(signed char *out, long long cap, int enable) {
+  long long n = g_ls_trace_n < cap ? g_ls_trace_n : cap;
+  if (out && g_ls_trace) memcpy(out, g_ls_trace, (size_t)n);
+  if (enable && !g_ls_trace) g_ls_trace = (signed char *)malloc(LS_TRACE_MAX);
+  if (!enable && g_ls_trace) { free(g_ls_trace); g_ls_trace = NULL; }
+  g_ls_trace_n = 0;
+  return n;
+}
 
 static solve_info q_opt(const omodel *m, const osched *s, int mode, owork *w, const REAL *q0, const REAL *lb, const REAL *ub,
                         const uint8_t *qmask, const REAL *kp, const REAL *kpmask, const REAL *site_pos,
@@ -621,6 +636,8 @@ static solve_info q_opt(const omodel *m, const osched *s, int mode, owork *w, co
 #pragma omp atomic
 #endif
     g_ls_hist[halvings > 16 ? 16 : halvings]++;
+    if (info.iters == 0) ls_trace_push(-1);
+    ls_trace_push(halvings);
     step = (st <= R(1e-6)) ? R(1) : st / R(0.5);
     REAL tn = R(0.5) * (R(1) + r_sqrt(mode ? r_fma(R(4) * t, t, R(1)) : R(1) + R(4) * t * t));
     REAL beta = (t - R(1)) / tn;
@@ -829,10 +846,9 @@ static int m_phase(const omodel *m, int mode, const REAL *kp, const REAL *q, con
         REAL e = r_fma(z.z, z.z, r_fma(z.y, z.y, z.x * z.x));
         int l = pos / s->spl, i = pos % s->spl;
         zz[l] = (i == 0) ? e : zz[l] + e;
-      } else zf = zf + (z.x * z.x + z.y * z.y + z.z * z.z);
+      } else part[3 * K] = part[3 * K] + (z.x * z.x + z.y * z.y + z.z * z.z);  /* mode 0: one running sum over sites and frames */
     }
-    if (mode) zf = butterfly32(zz);
-    part[3 * K] = first ? zf : part[3 * K] + zf;
+    if (mode) { zf = butterfly32(zz); part[3 * K] = first ? zf : part[3 * K] + zf; }
     if (mode && (t % MCH == MCH - 1 || t == T - 1)) {  /* chunk complete */
       int c0 = (t / MCH) == 0;
       for (int j = 0; j <= 3 * K; j++) tot[j] = c0 ? part[j] : tot[j] + part[j];

@@ -292,14 +292,17 @@ static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
   {
     // register-resident solver: latency mode (2 * NC warps per chain) for few chains, throughput mode (one warp per chain)
     // for many, dense throughput mode (registers capped for 16 warps per SM) from 16 chains per SM
-    // measured on B200 (profiles/mode_sweep_r2a.txt): latency mode wins while two CTAs per SM hold every chain, one warp per chain
-    // while 8 warps per SM do, the dense variant (16 warps per SM) beyond that
-    int sched = (a.C <= 2 * sms) ? 1 : (a.C > 8 * sms ? 2 : 0);
+    // measured on B200 (profiles/mode_sweep_r2a.txt, mode_sweep_r2c.txt): latency mode wins up to one chain per SM, one warp per
+    // chain while 8 warps per SM hold every chain, the dense variant (16 warps per SM) beyond that
+    // and the pair mode (two warps per chain) in between, from more than one chain per SM up to four pairs per SM
+    int sched = (a.C <= sms) ? 1 : (a.C <= 4 * sms ? 4 : (a.C > 8 * sms ? 2 : 0));
     if (g_force_mode >= 0) sched = g_force_mode;
-    const int nc = sched == 1 ? 2 : (sched == 3 ? 3 : 0);
+    const int nc = sched == 1 ? 2 : (sched == 3 ? 3 : (sched == 4 ? 1 : 0));
     const size_t area = ((size_t)2 * t->T.nqp + 7 * (size_t)t->T.pqn) * 4;
     const int block = nc ? 64 * nc : 128;
     const size_t smem = nc ? area + 8192 : 4 * area;  // latency mode: + the exchange area of solve_coop (< 8 KB for 4 slots, NC <= 3)
+    // persistent CTAs pull chains from the work counter; an unbalanced tail wave is kept on purpose: it runs at lower occupancy and
+    // therefore faster per chain than a balanced one would (profiles/mode_sweep_r2c.txt)
     const int grid = nc ? std::min(a.C, sms * 8) : std::min((a.C + 3) / 4, sms * 16);
 #define X(j, r, f) \
   if (fits_fast(t, j, r, f)) { CUDA_TRY(launch_fast_pose_##j##_##r##_##f(t->T, a, grid, block, smem, sched, s)); return STACB_OK; }
@@ -452,8 +455,8 @@ extern "C" int stacb_fma_peak(float *out, int blocks, int threads, int iters, vo
 }
 
 extern "C" int stacb_tree_set_mode(stacb_tree *t, int mode) {
-  if (!t || mode < -1 || mode > 6)
-    return fail(STACB_E_INVALID, "stacb_tree_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency), 2 (dense throughput) or 3 (wide latency)");
+  if (!t || mode < -1 || mode > 4)
+    return fail(STACB_E_INVALID, "stacb_tree_set_mode: mode must be -1 (auto), 0 (throughput), 1 (latency), 2 (dense throughput), 3 (wide latency) or 4 (pair)");
   t->mode.store(mode);
   return STACB_OK;
 }

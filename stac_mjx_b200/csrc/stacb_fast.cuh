@@ -68,7 +68,8 @@ template <int JM>
 struct Fwd {
   V3 P; Q4 Q;          // world pose of the lane's body
   Q4 Qp;               // world quaternion of its parent
-  V3 anc[JM], ax[JM];  // parent-frame anchor / axis of hinge slots >= 1 (slot 0 is a lane constant)
+  V3 lp[JM]; Q4 lq[JM]; // parent-frame pose of the body BEFORE hinge slot j >= 1 is applied (the reverse sweep derives that hinge's
+                        // anchor and axis from it; slot 0's are lane constants)
   V3 s, res;           // marker site position and masked residual (site lanes)
   V3 fpos; Q4 fq; float frinv;  // free joint: position, normalised quaternion, reciprocal of the normalisation divisor
 };
@@ -140,7 +141,7 @@ __device__ __forceinline__ void site_mask_kp(SiteC &st, const uint8_t *__restric
 
 // Forward half of q_loss (stac_core.py:27-63) at the point `pt` (solver layout, already merged with q0 by make_qs).
 // RT = pointer-jumping rounds of the kernel variant (>= ceil(log2(depth)); surplus rounds compose with the identity).
-template <int JM, int RT, bool KEEP>
+template <int JM, int RT>
 __device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &st, bool has_free, const float (&pt)[JM + 1], Fwd<JM> &S) {
   // free joint: every lane normalises the same seven values (broadcast from lanes 0..6)
   if (has_free) {
@@ -148,7 +149,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &s
 #pragma unroll
     for (int i = 0; i < 7; i++) fr[i] = __shfl_sync(FULL, pt[JM], i);
     S.fpos = mk3(fr[0], fr[1], fr[2]);
-    S.fq = normalize4(mk4(fr[3], fr[4], fr[5], fr[6]), &S.frinv);
+    S.fq = normalize4_nr(mk4(fr[3], fr[4], fr[5], fr[6]), &S.frinv);
   } else {
     S.fpos = mk3(0.f, 0.f, 0.f); S.fq = mk4(1.f, 0.f, 0.f, 0.f); S.frinv = 1.f;
   }
@@ -164,7 +165,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &s
   quat = sel4(L.pfree, S.fq, quat);
 #pragma unroll
   for (int j = 1; j < JM; j++) {  // further hinges of the same body
-    if (KEEP) { S.anc[j] = add3(pos, rotq(L.jps[j], quat)); S.ax[j] = rotq(L.jax[j], quat); }
+    S.lp[j] = pos; S.lq[j] = quat;
     ct = fmaf(ch[j], ch[j], -(sh[j] * sh[j]));
     sn = 2.0f * (sh[j] * ch[j]);
     const float om = 1.0f - ct;
@@ -220,7 +221,10 @@ __device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &
   const V3 Fp = rotq(F, pc), Tp = rotq(T0, pc);
   g[0] = dot3(L.ax[0], sub3(Tp, cross3(L.anc[0], Fp)));
 #pragma unroll
-  for (int j = 1; j < JM; j++) g[j] = dot3(S.ax[j], sub3(Tp, cross3(S.anc[j], Fp)));
+  for (int j = 1; j < JM; j++) {  // anchor / axis of hinge slot j in the parent frame, from the pose the forward pass kept
+    const V3 anc = add3(S.lp[j], rotq(L.jps[j], S.lq[j])), ax = rotq(L.jax[j], S.lq[j]);
+    g[j] = dot3(ax, sub3(Tp, cross3(anc, Fp)));
+  }
   g[JM] = 0.f;
   if (free_wanted) {  // uniform
     float wf[6];  // the free joint's subtree is its body's subtree: that lane's wrench
@@ -298,6 +302,28 @@ __device__ __forceinline__ bool free_wanted_of(const Uni &u, unsigned maskbits) 
   return u.has_free && __any_sync(FULL, u.lane < 7 && ((maskbits >> JM) & 1u));
 }
 
+// Per-solve view of the slots.  A coordinate the solve does not optimise ("frozen": valid, mask bit clear) has zero gradient: the
+// reference's iteration moves it to clip(q0) once and make_qs discards it afterwards.  Here it simply stays at q0 -- unbounded
+// effective box, gradient multiplied by gm = 0, so no select is needed anywhere in the iteration -- and the squared length of that
+// one move, which enters the first line search, is returned (0 whenever q0 is inside the box).
+template <int NS>
+struct SolveC { float lb[NS], ub[NS], gm[NS]; };
+
+template <int NS>
+__device__ __forceinline__ float solve_setup(const Slots<NS> &co, const float (&q0)[NS], unsigned maskbits, SolveC<NS> &sc) {
+  const float inf = __int_as_float(0x7f800000);
+  float dn[NS];
+#pragma unroll
+  for (int m = 0; m < NS; m++) {
+    const bool bit = (maskbits >> m) & 1u, frozen = co.valid[m] && !bit;
+    sc.gm[m] = bit ? 1.0f : 0.0f;
+    sc.lb[m] = frozen ? -inf : co.lb[m];
+    sc.ub[m] = frozen ? inf : co.ub[m];
+    dn[m] = frozen ? clipm(q0[m], co.lb[m], co.ub[m]) - q0[m] : 0.0f;
+  }
+  return warp_sum(lane_dot<NS>(dn, dn));
+}
+
 // ------------------------------------------------------------------------------------------
 // jaxopt 0.8.5 ProjectedGradient.run (ProximalGradient._update_accel / _ls / _error with the box projection), one warp.
 // Two-state machine so the kernel holds ONE forward and ONE reverse evaluation:
@@ -305,7 +331,7 @@ __device__ __forceinline__ bool free_wanted_of(const Uni &u, unsigned maskbits) 
 //   state LS: the point is a candidate x+ -> loss; rejected: halve the step; accepted: gradient at x+ from the state of
 //             this same evaluation (the reference recomputes FK there: same values), error, next y.
 //   sqp: squared distance the projection moves the PASSIVE coordinates in the first iteration (they have zero gradient:
-//        x+ = clip(q0) from then on; zero whenever q0 is inside the box).
+//        x+ = clip(q0) from then on; zero whenever q0 is inside the box); the frozen slots' share is added here (solve_setup).
 // ------------------------------------------------------------------------------------------
 template <int JM, int RT>
 __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &st, const Uni &u, const Slots<JM + 1> &co, const float (&q0)[JM + 1],
@@ -313,7 +339,7 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
   constexpr int NS = JM + 1;
   float y[NS], g[NS], xn[NS], d[NS], gt[NS];
 #pragma unroll
-  for (int m = 0; m < NS; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; xn[m] = x[m]; g[m] = 0.f; gt[m] = 0.f; }
+  for (int m = 0; m < NS; m++) { x[m] = q0[m]; y[m] = x[m]; xn[m] = x[m]; g[m] = 0.f; gt[m] = 0.f; }
   float t = 1.0f, step = 1.0f, stp = 1.0f, fy = 0.f, sq = 0.f, dg = 0.f;
   int halv = 0;
   bool in_ls = false;
@@ -321,12 +347,14 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
   out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
   if (u.maxiter <= 0) return out;
   const bool fw = free_wanted_of<JM>(u, maskbits);
+  SolveC<NS> sc;
+  sqp = solve_setup<NS>(co, q0, maskbits, sc) + sqp;
   Fwd<JM> S;
   for (;;) {
     float pt[NS];
 #pragma unroll
-    for (int m = 0; m < NS; m++) pt[m] = ((maskbits >> m) & 1u) ? (in_ls ? xn[m] : y[m]) : q0[m];
-    const float f = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+    for (int m = 0; m < NS; m++) pt[m] = in_ls ? xn[m] : y[m];
+    const float f = eval_fwd<JM, RT>(L, st, u.has_free, pt, S);
     bool rejected = false;
     if (in_ls) {
       out.ls++;
@@ -338,14 +366,14 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
     if (!rejected) {
       eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
 #pragma unroll
-      for (int m = 0; m < NS; m++) gt[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? gt[m] : 0.f;
+      for (int m = 0; m < NS; m++) gt[m] = gt[m] * sc.gm[m];
       if (in_ls) {  // accepted x+ = xn
         step = (stp <= 1e-6f) ? 1.0f : stp / 0.5f;
         const float beta = beta_of(u.betas, out.iters, t);
 #pragma unroll
         for (int m = 0; m < NS; m++) {
           y[m] = fmaf(beta, xn[m] - x[m], xn[m]);
-          d[m] = clipm(xn[m] - gt[m], co.lb[m], co.ub[m]) - xn[m];
+          d[m] = clipm(xn[m] - gt[m], sc.lb[m], sc.ub[m]) - xn[m];
           x[m] = xn[m];
         }
         out.err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
@@ -367,7 +395,7 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
     }
 #pragma unroll
     for (int m = 0; m < NS; m++) {
-      xn[m] = clipm(fmaf(-stp, g[m], y[m]), co.lb[m], co.ub[m]);
+      xn[m] = clipm(fmaf(-stp, g[m], y[m]), sc.lb[m], sc.ub[m]);
       d[m] = xn[m] - y[m];
     }
     sq = lane_dot<NS>(d, d);
@@ -397,21 +425,21 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
   constexpr int NS = JM + 1;
   float y[NS], g[NS], gt[NS], xj[NS], pt[NS], d[NS];
 #pragma unroll
-  for (int m = 0; m < NS; m++) { x[m] = co.valid[m] ? q0[m] : 0.f; y[m] = x[m]; g[m] = 0.f; }
+  for (int m = 0; m < NS; m++) { x[m] = q0[m]; y[m] = x[m]; g[m] = 0.f; }
   SolveOut out;
   out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
   if (u.maxiter <= 0) return out;
   const bool fw = free_wanted_of<JM>(u, maskbits);
   const int j = w % NC;
   const bool isY = w >= NC;
+  SolveC<NS> sc;
+  sqp = solve_setup<NS>(co, q0, maskbits, sc) + sqp;
   Fwd<JM> S;
   // f(y0), grad f(y0): every warp computes them (identical values)
-#pragma unroll
-  for (int m = 0; m < NS; m++) pt[m] = ((maskbits >> m) & 1u) ? y[m] : q0[m];
-  float fy = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+  float fy = eval_fwd<JM, RT>(L, st, u.has_free, y, S);
   eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, g);
 #pragma unroll
-  for (int m = 0; m < NS; m++) g[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? g[m] : 0.f;
+  for (int m = 0; m < NS; m++) g[m] = g[m] * sc.gm[m];
   float t = 1.0f, stp = 1.0f;
   float beta = beta_of(u.betas, 0, t);
   int base = 0;
@@ -422,10 +450,9 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     float sq = 0.f, dg = 0.f;
 #pragma unroll
     for (int m = 0; m < NS; m++) {
-      xj[m] = clipm(fmaf(-sj, g[m], y[m]), co.lb[m], co.ub[m]);
+      xj[m] = clipm(fmaf(-sj, g[m], y[m]), sc.lb[m], sc.ub[m]);
       d[m] = xj[m] - y[m];
-      const float p = isY ? fmaf(beta, xj[m] - x[m], xj[m]) : xj[m];
-      pt[m] = ((maskbits >> m) & 1u) ? p : q0[m];
+      pt[m] = isY ? fmaf(beta, xj[m] - x[m], xj[m]) : xj[m];
     }
     if (!isY) {
       sq = lane_dot<NS>(d, d);
@@ -433,16 +460,16 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
       warp_sum2(sq, dg);
       sq = sq + sqp;
     }
-    const float f = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+    const float f = eval_fwd<JM, RT>(L, st, u.has_free, pt, S);
     eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
 #pragma unroll
-    for (int m = 0; m < NS; m++) gt[m] = (co.valid[m] && ((maskbits >> m) & 1u)) ? gt[m] : 0.f;
+    for (int m = 0; m < NS; m++) gt[m] = gt[m] * sc.gm[m];
     if (!isY) {
       const float dec = sj * (f - fy);
       const float cond = fmaf(sj, dg, 0.5f * sq);
       const bool rejected = (dec > cond + 1.1920929e-07f) && (base + j < u.maxls);
 #pragma unroll
-      for (int m = 0; m < NS; m++) d[m] = clipm(xj[m] - gt[m], co.lb[m], co.ub[m]) - xj[m];
+      for (int m = 0; m < NS; m++) d[m] = clipm(xj[m] - gt[m], sc.lb[m], sc.ub[m]) - xj[m];
       const float err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
       if (u.lane == 0) {
         xc->acc[par][j] = rejected ? 0.f : 1.f;
@@ -475,7 +502,7 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
     for (int i = 0; i < NC - 1; i++) sk = (i < k) ? sk * 0.5f : sk;
 #pragma unroll
     for (int m = 0; m < NS; m++) {
-      const float xk = clipm(fmaf(-sk, g[m], y[m]), co.lb[m], co.ub[m]);
+      const float xk = clipm(fmaf(-sk, g[m], y[m]), sc.lb[m], sc.ub[m]);
       y[m] = fmaf(beta, xk - x[m], xk);
       x[m] = xk;
     }
@@ -493,6 +520,118 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
   return out;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Pair mode: TWO warps cooperate on one chain -- for chain counts between the latency regime (few chains: 2 * NC warps each) and
+// the throughput regime (one warp each).  Per FISTA iteration
+//   phase A: warp 0 / warp 1 evaluate the line-search candidates x+_a (step s) and x+_b (step s / 2) at the same time (forward
+//            only); none accepted: next two step sizes;
+//   phase B: the warp that evaluated the accepted candidate turns its forward state into grad f(x+) (stopping criterion) while
+//            its partner evaluates the extrapolation y' and grad f(y') for the next iteration.
+// Critical path 2 forward + 1 reverse evaluations instead of 3 + 2, at the instruction budget of the one-warp solver (no
+// speculation on y').  Same arithmetic, same accepted candidate: bit-identical to `solve`.
+// ------------------------------------------------------------------------------------------
+template <int NS>
+struct XchgPair {  // shared memory
+  float g[32 * NS];
+  float acc[2][2], nf[2][2];  // [parity][warp]: accepted flag, non-finite loss flag of the two candidates
+  float err, fy;
+};
+
+template <int JM, int RT>
+__device__ __forceinline__ SolveOut solve_pair(const LaneC<JM, RT> &L, const SiteC &st, const Uni &u, const Slots<JM + 1> &co, const float (&q0)[JM + 1],
+                                               unsigned maskbits, float sqp, float (&x)[JM + 1], XchgPair<JM + 1> *xc, int w, int &par) {
+  constexpr int NS = JM + 1;
+  float y[NS], g[NS], gt[NS], xj[NS], d[NS];
+#pragma unroll
+  for (int m = 0; m < NS; m++) { x[m] = q0[m]; y[m] = x[m]; g[m] = 0.f; }
+  SolveOut out;
+  out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
+  if (u.maxiter <= 0) return out;
+  const bool fw = free_wanted_of<JM>(u, maskbits);
+  SolveC<NS> sc;
+  sqp = solve_setup<NS>(co, q0, maskbits, sc) + sqp;
+  Fwd<JM> S;
+  float fy = eval_fwd<JM, RT>(L, st, u.has_free, y, S);  // f(y0), grad f(y0): both warps (identical values)
+  eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, g);
+#pragma unroll
+  for (int m = 0; m < NS; m++) g[m] = g[m] * sc.gm[m];
+  float t = 1.0f, stp = 1.0f;
+  int base = 0;
+  for (;;) {
+    // phase A: this warp's line-search candidate
+    const float sj = w ? stp * 0.5f : stp;
+    float sq, dg;
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+      xj[m] = clipm(fmaf(-sj, g[m], y[m]), sc.lb[m], sc.ub[m]);
+      d[m] = xj[m] - y[m];
+    }
+    sq = lane_dot<NS>(d, d);
+    dg = lane_dot<NS>(d, g);
+    warp_sum2(sq, dg);
+    sq = sq + sqp;
+    const float f = eval_fwd<JM, RT>(L, st, u.has_free, xj, S);
+    const float dec = sj * (f - fy);
+    const float cond = fmaf(sj, dg, 0.5f * sq);
+    const bool rejected = (dec > cond + 1.1920929e-07f) && (base + w < u.maxls);
+    if (u.lane == 0) {
+      xc->acc[par][w] = rejected ? 0.f : 1.f;
+      xc->nf[par][w] = (f - f == 0.0f) ? 0.f : 1.f;
+    }
+    __syncthreads();
+    const bool a0 = xc->acc[par][0] != 0.f, a1 = xc->acc[par][1] != 0.f;
+    const int k = a0 ? 0 : (a1 ? 1 : -1);
+    if (xc->nf[par][0] != 0.f || (k != 0 && xc->nf[par][1] != 0.f)) out.bad = true;  // candidates the sequential search evaluates
+    par ^= 1;
+    if (k < 0) {  // both rejected: next two step sizes
+      base += 2;
+      stp = stp * 0.25f;
+      continue;
+    }
+    out.ls += base + k + 1;
+    const float sk = k ? stp * 0.5f : stp;
+    const float beta = beta_of(u.betas, out.iters, t);
+    // phase B
+    if (w == k) {  // gradient at the accepted x+ (this warp's forward state) -> unit-step fixed-point residual
+      eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
+#pragma unroll
+      for (int m = 0; m < NS; m++) {
+        gt[m] = gt[m] * sc.gm[m];
+        d[m] = clipm(xj[m] - gt[m], sc.lb[m], sc.ub[m]) - xj[m];
+      }
+      const float err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
+      if (u.lane == 0) xc->err = err;
+#pragma unroll
+      for (int m = 0; m < NS; m++) { y[m] = fmaf(beta, xj[m] - x[m], xj[m]); x[m] = xj[m]; }
+    } else {  // the partner: x+_k, the extrapolation y', f(y') and grad f(y')
+#pragma unroll
+      for (int m = 0; m < NS; m++) {
+        const float xk = clipm(fmaf(-sk, g[m], y[m]), sc.lb[m], sc.ub[m]);
+        y[m] = fmaf(beta, xk - x[m], xk);
+        x[m] = xk;
+      }
+      const float fyn = eval_fwd<JM, RT>(L, st, u.has_free, y, S);
+      eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
+#pragma unroll
+      for (int m = 0; m < NS; m++) xc->g[32 * m + u.lane] = gt[m] * sc.gm[m];
+      if (u.lane == 0) xc->fy = fyn;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < NS; m++) g[m] = xc->g[32 * m + u.lane];
+    fy = xc->fy;
+    out.err = xc->err;
+    stp = (sk <= 1e-6f) ? 1.0f : sk / 0.5f;
+    out.iters++;
+    sqp = 0.f;
+    base = 0;
+    // no third barrier: the next writes of g / fy / err come after the NEXT phase-A barrier, which a warp reaches only once it has
+    // read this iteration's values; the accept flags alternate between two parities
+    if (!(out.err > u.tol && out.iters < u.maxiter)) break;
+  }
+  return out;
+}
 
 // ------------------------------------------------------------------------------------------
 // solver slots <-> qpos addresses
@@ -603,6 +742,7 @@ __device__ __forceinline__ void outputs_from_qbuf(const Chain &ch, const SiteC &
 // ------------------------------------------------------------------------------------------
 
 // NC == 0: throughput mode, one warp per chain, four chains per CTA (MINB CTAs per SM requested from the compiler);
+// NC == 1: pair mode, two warps per chain, one chain per 64-thread CTA (solve_pair);
 // NC >= 2: latency mode, 2 * NC warps cooperate on one chain (solve_coop).
 template <int JM, int RT, int NBF, int NC, int MINB>
 __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(DevTree T, PoseArgs a) {
@@ -617,6 +757,7 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
   const int area = 2 * T.nqp + 7 * T.pqn;  // qbuf [nqp], (unused) [nqp], PQ [7 pqn]
   Chain ch(T, smem + (size_t)(COOP ? 0 : wib) * area, nullptr, lane, 0, 1, 0);
   Xchg<NS, (NC > 0 ? NC : 1)> *xc = reinterpret_cast<Xchg<NS, (NC > 0 ? NC : 1)> *>(smem + area);
+  XchgPair<NS> *xp = reinterpret_cast<XchgPair<NS> *>(smem + area);
   const bool writer = !COOP || wib == 0;
   LaneC<JM, RT> L;
   lane_init<JM, RT>(L, T, lane);
@@ -677,7 +818,8 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
       }
       const float sqp = npassive ? passive_sq(T, lane, ch.qbuf, a.lb, a.ub) : 0.f;
       SolveOut so;
-      if constexpr (COOP) so = solve_coop<JM, RT, NC>(L, st, u, co, q0, bits, sqp, x, xc, wib, par);
+      if constexpr (NC == 1) so = solve_pair<JM, RT>(L, st, u, co, q0, bits, sqp, x, xp, wib, par);
+      else if constexpr (COOP) so = solve_coop<JM, RT, NC>(L, st, u, co, q0, bits, sqp, x, xc, wib, par);
       else so = solve<JM, RT>(L, st, u, co, q0, bits, sqp, x);
 #pragma unroll
       for (int m = 0; m < NS; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];  // utils.make_qs
@@ -754,7 +896,7 @@ __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a)
 #pragma unroll
       for (int m = 0; m < NS; m++) pt[m] = ((bits >> m) & 1u) ? q[m] : q0[m];
       Fwd<JM> S;
-      const float loss = eval_fwd<JM, RT, true>(L, st, u.has_free, pt, S);
+      const float loss = eval_fwd<JM, RT>(L, st, u.has_free, pt, S);
       if (lane == 0) a.out_a[b] = loss;
       if (a.out_b) {
         eval_bwd<JM, RT>(L, S, lane, free_wanted_of<JM>(u, bits), u.free_e, g);
@@ -769,6 +911,11 @@ __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a)
       float x[NS];
       const float sqp = T.npassive ? passive_sq(T, lane, qb, a.lb, a.ub) : 0.f;
       const SolveOut so = solve<JM, RT>(L, st, u, co, q, bits, sqp, x);
+      if (u.maxiter > 0) {  // res.params of the coordinates the solve does not optimise: the reference's iterate sits at clip(q0)
+#pragma unroll
+        for (int m = 0; m < NS; m++)
+          if (co.valid[m] && !((bits >> m) & 1u)) x[m] = clipm(x[m], co.lb[m], co.ub[m]);
+      }
       float *po = a.out_a + (size_t)b * nq;
       for (int i = lane; i < T.npassive; i += 32) {
         const int p = __ldg(T.passive + i);

@@ -18,14 +18,13 @@ static cudaError_t launch(K k, const DevTree &T, const PoseArgs &a, int grid, in
   return cudaGetLastError();
 }
 
-// sched: 0 throughput, 1 latency with 4 warps per chain, 2 dense throughput, 3 latency with 6 warps per chain
+// sched: 0 throughput, 1 latency with 4 warps per chain, 2 dense throughput, 3 latency with 6 warps per chain, 4 pair mode (2 warps per chain)
 cudaError_t FN(launch_fast_pose_, V_FJM, V_FRT, V_FNBF)(const DevTree &T, const PoseArgs &a, int grid, int block, size_t smem, int sched, cudaStream_t s) {
   switch (sched) {
     case 1: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 2, 1>, T, a, grid, block, smem, s);
     case 3: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 3, 1>, T, a, grid, block, smem, s);
     case 2: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 4>, T, a, grid, block, smem, s);
-    case 5: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 3>, T, a, grid, block, smem, s);
-    case 6: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 2>, T, a, grid, block, smem, s);
+    case 4: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 1, 1>, T, a, grid, block, smem, s);
     default: return launch(fast::fast_pose_kernel<V_FJM, V_FRT, V_FNBF, 0, 1>, T, a, grid, block, smem, s);
   }
 }

@@ -80,6 +80,22 @@ __device__ __forceinline__ void sincos_canon(float x, float *sp, float *cp) {
   *cp = co;
 }
 
+// The same normalisation with a division-free reciprocal square root that is REPRODUCIBLE on a CPU (no MUFU approximation):
+// the classic integer seed, two Newton steps r <- r (1.5 - h r^2) and a final one in residual form r <- r + (r / 2)(1 - n2 r^2), all
+// plain fused multiply-adds (within 1.3 ulp of 1 / sqrt(n2)); a zero quaternion maps to zero as with math.normalize.
+// *rinv_out = 1 / |q| (the reverse sweep uses it).
+__device__ __forceinline__ Q4 normalize4_nr(Q4 q, float *rinv_out) {
+  const float n2 = fmaf(q.z, q.z, fmaf(q.y, q.y, fmaf(q.x, q.x, q.w * q.w)));
+  const float h = 0.5f * n2;
+  float r = __int_as_float(0x5f3759df - (__float_as_int(n2) >> 1));
+#pragma unroll
+  for (int i = 0; i < 2; i++) r = r * fmaf(-(h * r), r, 1.5f);
+  const float e = fmaf(-(n2 * r), r, 1.0f);
+  r = fmaf(0.5f * r, e, r);
+  *rinv_out = r;
+  return mk4(q.w * r, q.x * r, q.y * r, q.z * r);
+}
+
 // sin/cos up to a COMMON sign: 3-term Cody-Waite reduction by pi, then degree-9 / degree-8 minimax polynomials on
 // [-pi/2, pi/2] (sin within 2 ulp, cos within 1 ulp of 1).  Returns ((-1)^j sin x, (-1)^j cos x) with j = rint(x / pi):
 // a hinge's half-angle pair enters FK only through products of two of its members (cos t, sin t) and through the

@@ -142,7 +142,7 @@ def test_latency_and_throughput_modes_are_bit_identical(name, engine_of):
     kp = kp.reshape(5, F, -1)
     outs = []
     try:
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3) + ((4,) if eng.path == 1 else ()):  # 4 = pair mode of the register-resident path
             eng.set_mode(mode)
             qio = torch.tensor(np.tile(c.tree.qpos0.astype(np.float32), (5, 1)), device=eng.device)
             o = eng.pose_clips(kp, qio, c.setup.initial_offsets, c.setup.lb, c.setup.ub, c.setup.indiv_parts, **c.root_kw())
@@ -207,7 +207,7 @@ def test_passive_coordinates_outside_their_box(rodent, engine_of):
     q0[1, -5] -= 7.0
     ref = rodent.oracle(np.float32, 2).pose_clips(kp, q0, s.initial_offsets, s.lb, s.ub, s.indiv_parts, nthreads=2, **rodent.root_kw())
     try:
-        for mode in (0, 1, 3):
+        for mode in (0, 1, 3, 4):
             eng.set_mode(mode)
             qio = torch.tensor(q0, device=eng.device)
             out = eng.pose_clips(kp, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **rodent.root_kw())

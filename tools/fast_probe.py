@@ -46,7 +46,7 @@ kpc = kp.reshape(nclip, F, -1)[:, :Fs].copy()
 kw = dict(do_root=1 if has_root else 0, root_kp_idx=s.root_kp_idx, trunk_kps=s.trunk_kps, tol=tol)
 qinit = np.tile(t.qpos0.astype(np.float32), (nclip, 1)); qinit[:, -1] += 10.0
 ref = orc.pose_clips(kpc, qinit, off, s.lb, s.ub, s.indiv_parts, nthreads=8, **kw)
-for mode in (0, 1, 2, 3):
+for mode in (0, 1, 2, 3, 4):
     eng.set_mode(mode)
     qio = torch.tensor(qinit, device="cuda")
     out = eng.pose_clips(kpc, qio, off, s.lb, s.ub, s.indiv_parts, **kw)
@@ -58,7 +58,7 @@ for mode in (0, 1, 2, 3):
 for C in [int(a) for a in sys.argv[2:]] or [72]:
     kpb, _, _ = synth.synth_session(t, s, C * F, F, seed=7)
     kpd = torch.tensor(kpb.reshape(C, F, -1), device="cuda")
-    for path, mode in ((0, 1), (0, 3), (0, 0), (0, 2), (1, 1), (1, 0)):
+    for path, mode in ((0, 1), (0, 3), (0, 4), (0, 0), (0, 2), (1, 1), (1, 0)):
         eng.set_path(path); eng.set_mode(mode)
         qio = torch.tensor(np.tile(t.qpos0.astype(np.float32), (C, 1)), device="cuda")
         o = eng.pose_clips(kpd[:, :5].contiguous(), qio.clone(), off, s.lb, s.ub, s.indiv_parts, **kw)

@@ -24,9 +24,12 @@ for C in chains:
         qio = torch.tensor(np.tile(t.qpos0.astype(np.float32), (C, 1)), device="cuda")
         eng.pose_clips(kpd[:, :3].contiguous(), qio.clone(), s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        o = eng.pose_clips(kpd, qio, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        print(f"{name} C={C} mode {mode}: {ms:.1f} ms -> {C*F/ms*1e3:.0f} frames/s", flush=True)
+        best = 1e30
+        for rep in range(2):
+            q2 = qio.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            o = eng.pose_clips(kpd, q2, s.initial_offsets, s.lb, s.ub, s.indiv_parts, **kw)
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(f"{name} C={C} mode {mode}: {best:.1f} ms -> {C*F/best*1e3:.0f} frames/s", flush=True)
