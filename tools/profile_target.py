@@ -15,6 +15,9 @@ kpn = list(cfg.model.KEYPOINT_MODEL_PAIRS.keys())
 s = model.make_setup(tree, cfg.model, kpn)
 kp, _, _ = synth.synth_session(tree, s, C * F, F, seed=1)
 eng = Engine(tree, s.site_bodies, 0)
+import os
+eng.set_mode(int(os.environ.get("STACB_MODE", "-1")))
+eng.set_path(int(os.environ.get("STACB_PATH", "0")))
 has_root = s.root_kp_idx >= 0 and int(tree.jnt_type[0]) in (0, 2)
 for _ in range(3):
     qio = torch.tensor(np.tile(tree.qpos0.astype(np.float32), (C, 1)), device="cuda")

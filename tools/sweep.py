@@ -36,9 +36,10 @@ for spec in sys.argv[1:]:
     it, ls = int(o["iters"].sum()) + int(o["root_stats"][:, [0, 2]].sum()), int(o["ls_evals"].sum()) + int(o["root_stats"][:, [1, 3]].sum())
     pc = flops.path_cost(tree, s.site_bodies)
     fl = pc.total(it, ls, C * F, 1 + s.indiv_parts.shape[0])
+    fl_exec = pc.executed(it, ls, C * F, 1 + s.indiv_parts.shape[0])
     resid = float(torch.linalg.norm(o["sites"] - kpd.reshape(C, F, -1, 3), dim=-1).mean())
     print(json.dumps({"model": name, "frames": C * F, "clips": C, "clip_frames": F, "ms": ms, "frames_per_s": C * F / ms * 1e3,
-                      "iters_per_frame": it / (C * F), "ls_per_iter": ls / max(it, 1), "tflops_algorithmic": fl / ms / 1e9,
+                      "iters_per_frame": it / (C * F), "ls_per_iter": ls / max(it, 1), "tflops_algorithmic": fl / ms / 1e9, "tflops_executed": fl_exec / ms / 1e9, "path": "register-resident" if eng.path else "general",
                       "mean_marker_residual_m": resid, "nonfinite": int((o["status"] != 0).sum())}), flush=True)
     del eng, kpd, out, o
     torch.cuda.empty_cache()
