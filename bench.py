@@ -363,6 +363,16 @@ def run_ours(args):
     except Exception:
         pass
     hbm_step = flops.hbm_bytes_per_frame(tree, K, 1 + P) * A.C * A.F
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic_r2c_bench_launch.csv"
+    if tfile.exists() and args.model == "rodent" and A.C * A.F == 18000:
+        try:
+            import csv
+
+            vals = {r[12]: float(r[14]) for r in csv.reader(tfile.open()) if len(r) > 14 and r[12].startswith("dram__bytes")}
+            traffic = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+        except Exception:
+            traffic = None
 
     cpu = parity = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
@@ -410,9 +420,10 @@ def run_ours(args):
             "roofline": {
                 **roof,
                 "peak_nominal": sms * 128 * 2 * (sampler.summary().get("sm_max_mhz") or 1965.0) * 1e6 / 1e12,
-                "traffic": None,
-                "traffic_note": "not measured in-run; ncu dram read+write of one bench-size launch of the previous kernel revision was 6.9 MB "
-                                "(profiles/traffic_r1f_bench_launch.csv) against 50 MB algorithmic bytes: outputs mostly stay in the 126 MB L2",
+                "traffic": traffic,
+                "traffic_note": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel revision on this workload "
+                                "(72 clips x 250 frames) captured with ncu (profiles/traffic_r2c_bench_launch.csv; not measured in this run); below "
+                                "the 50 MB algorithmic bytes because most outputs are still in the 126 MB L2 when the kernel ends",
                 "note": "FP32 CUDA-core bound path (no tensor-core or HBM-bound kernel exists on it). achieved = flops_reference_sequence "
                         "(stac_mjx_b200/flops.py, SURVEY 8(d): the reference's operation sequence) of rank 0's launch / its CUDA-event duration; "
                         "achieved_executed counts only what the kernel's sequential semantics need (accepted candidate's FK reused, no phantom "
