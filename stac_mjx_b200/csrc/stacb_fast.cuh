@@ -414,11 +414,19 @@ __device__ __forceinline__ SolveOut solve(const LaneC<JM, RT> &L, const SiteC &s
 // arithmetic as in `solve`, so results are bit-identical to the one-warp solver.
 // ------------------------------------------------------------------------------------------
 template <int NS, int NC>
-struct Xchg {  // shared memory
-  float g[2][NC][32 * NS];
-  float acc[2][NC], err[2][NC], fy[2][NC], nf[2][NC];  // accepted flag, error at x+_j, f(y'_j), non-finite f(x+_j)
+struct Xchg {  // shared memory, [parity] double-buffered
+  float g[2][NC][32 * NS];  // Y warp j: grad f(y'_j)
+  float e[2][NC][32];       // X warp j: per-lane partial of |clip(x+_j - grad f(x+_j)) - x+_j|^2 (stopping criterion)
+  float fx[2][NC], fy[2][NC], sq[2][NC], dg[2][NC];  // f(x+_j) (X warp), f(y'_j) and the two line-search sums of candidate j (Y warp)
 };
 
+// The work of a round is split so that both roles carry about the same instruction count (the barrier waits for the slowest):
+//   X warp j: forward + reverse at x+_j, per-lane residual partials;
+//   Y warp j: the line-search sums |x+_j - y|^2, <x+_j - y, g> of candidate j, forward + reverse at y'(x+_j).
+// After the barrier every warp evaluates the accept conditions of all candidates from the exchanged scalars (same operations as the
+// sequential search).  The stopping criterion of an accepted iteration is reduced (butterfly + sqrt) while the NEXT round is being
+// evaluated and tested just before that round's barrier: when it fires, the round in flight is discarded -- nothing it computed has
+// touched the solver state yet -- so the result is the sequential solver's, one speculative round per converged solve later.
 template <int JM, int RT, int NC>
 __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const SiteC &st, const Uni &u, const Slots<JM + 1> &co, const float (&q0)[JM + 1],
                                                unsigned maskbits, float sqp, float (&x)[JM + 1], Xchg<JM + 1, NC> *xc, int w, int &par) {
@@ -443,53 +451,61 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
   float t = 1.0f, stp = 1.0f;
   float beta = beta_of(u.betas, 0, t);
   int base = 0;
+  bool pending = false;  // the last accepted iteration's stopping criterion has not been tested yet
+  float e_prev = 0.f;
   for (;;) {
     float sj = stp;
 #pragma unroll
     for (int i = 0; i < NC - 1; i++) sj = (i < j) ? sj * 0.5f : sj;
-    float sq = 0.f, dg = 0.f;
 #pragma unroll
     for (int m = 0; m < NS; m++) {
       xj[m] = clipm(fmaf(-sj, g[m], y[m]), sc.lb[m], sc.ub[m]);
       d[m] = xj[m] - y[m];
       pt[m] = isY ? fmaf(beta, xj[m] - x[m], xj[m]) : xj[m];
     }
-    if (!isY) {
-      sq = lane_dot<NS>(d, d);
-      dg = lane_dot<NS>(d, g);
+    if (isY) {
+      float sq = lane_dot<NS>(d, d), dg = lane_dot<NS>(d, g);
       warp_sum2(sq, dg);
       sq = sq + sqp;
+      if (u.lane == 0) { xc->sq[par][j] = sq; xc->dg[par][j] = dg; }
     }
     const float f = eval_fwd<JM, RT>(L, st, u.has_free, pt, S);
     eval_bwd<JM, RT>(L, S, u.lane, fw, u.free_e, gt);
 #pragma unroll
     for (int m = 0; m < NS; m++) gt[m] = gt[m] * sc.gm[m];
     if (!isY) {
-      const float dec = sj * (f - fy);
-      const float cond = fmaf(sj, dg, 0.5f * sq);
-      const bool rejected = (dec > cond + 1.1920929e-07f) && (base + j < u.maxls);
 #pragma unroll
       for (int m = 0; m < NS; m++) d[m] = clipm(xj[m] - gt[m], sc.lb[m], sc.ub[m]) - xj[m];
-      const float err = sqrtf(warp_sum(lane_dot<NS>(d, d)));
-      if (u.lane == 0) {
-        xc->acc[par][j] = rejected ? 0.f : 1.f;
-        xc->err[par][j] = err;
-        xc->nf[par][j] = (f - f == 0.0f) ? 0.f : 1.f;
-      }
+      xc->e[par][j][u.lane] = lane_dot<NS>(d, d);
+      if (u.lane == 0) xc->fx[par][j] = f;
     } else {
 #pragma unroll
       for (int m = 0; m < NS; m++) xc->g[par][j][32 * m + u.lane] = gt[m];
       if (u.lane == 0) xc->fy[par][j] = f;
     }
+    if (pending) {  // uniform over the CTA: every warp reduces the same partials in the same order
+      out.err = sqrtf(warp_sum(e_prev));
+      pending = false;
+      if (!(out.err > u.tol)) break;  // converged one round ago: the round in flight is dropped
+    }
     __syncthreads();
-    int k = -1;
-#pragma unroll
-    for (int i = NC - 1; i >= 0; i--) k = (xc->acc[par][i] != 0.f) ? i : k;
     const int rp = par;
     par ^= 1;
+    int k = -1;
+    bool nonfinite = false;
 #pragma unroll
-    for (int i = 0; i < NC; i++)  // non-finite losses among the candidates the sequential line search evaluates
-      if ((k < 0 || i <= k) && xc->nf[rp][i] != 0.f) out.bad = true;
+    for (int i = NC - 1; i >= 0; i--) {  // accept conditions of the sequential line search, candidate i = step / 2^i
+      float si = stp;
+#pragma unroll
+      for (int h = 0; h < NC - 1; h++) si = (h < i) ? si * 0.5f : si;
+      const float fi = xc->fx[rp][i];
+      const float dec = si * (fi - fy);
+      const float cond = fmaf(si, xc->dg[rp][i], 0.5f * xc->sq[rp][i]);
+      const bool rejected = (dec > cond + 1.1920929e-07f) && (base + i < u.maxls);
+      k = rejected ? k : i;
+      nonfinite = (!rejected) ? !(fi - fi == 0.0f) : (nonfinite || !(fi - fi == 0.0f));  // candidates 0..k (all when none is accepted)
+    }
+    if (nonfinite) out.bad = true;
     if (k < 0) {  // every candidate rejected: next NC step sizes
       base += NC;
 #pragma unroll
@@ -509,13 +525,17 @@ __device__ __forceinline__ SolveOut solve_coop(const LaneC<JM, RT> &L, const Sit
 #pragma unroll
     for (int m = 0; m < NS; m++) g[m] = xc->g[rp][k][32 * m + u.lane];
     fy = xc->fy[rp][k];
-    out.err = xc->err[rp][k];
+    e_prev = xc->e[rp][k][u.lane];
     stp = (sk <= 1e-6f) ? 1.0f : sk / 0.5f;
     out.iters++;
-    beta = beta_of(u.betas, out.iters, t);
     sqp = 0.f;
-    if (!(out.err > u.tol && out.iters < u.maxiter)) break;
     base = 0;
+    if (!(out.iters < u.maxiter)) {  // iteration cap: no further round, reduce the criterion now
+      out.err = sqrtf(warp_sum(e_prev));
+      break;
+    }
+    beta = beta_of(u.betas, out.iters, t);
+    pending = true;  // (a run-time choice between testing now and one round late was measured: it costs more than the round it saves)
   }
   return out;
 }
