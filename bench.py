@@ -329,6 +329,34 @@ def run_ours(args):
         }  # fmt: skip
         del B
         torch.cuda.empty_cache()
+    # ---------------- BASELINE config 4: fruitfly (deeper / wider tree: general kernels), one 18 000-frame session sharded by clip ----------------
+    if not args.no_extras:
+        try:
+            ftree, fcfg4, fsetup = load_case("fly_treadmill")
+            feng = Engine(ftree, fsetup.site_bodies, local)
+            fkw = root_kw(ftree, fcfg4, fsetup)
+            Cf = args.frames // args.clip
+            flo, fhi = parallel.shard_range(Cf, rank, ws)
+            fkp, _, _ = synth.synth_session(ftree, fsetup, Cf * args.clip, args.clip, seed=args.seed + 7)
+            fkp_dev = torch.from_numpy(np.ascontiguousarray(fkp.reshape(Cf, args.clip, -1)[flo:fhi])).to(dev)
+            fq0 = torch.tensor(np.tile(ftree.qpos0.astype(np.float32), (max(fhi - flo, 1), 1)), device=dev)[: fhi - flo]
+            fout = {}
+
+            def fstep():
+                if fhi > flo:
+                    feng.pose_clips(fkp_dev, fq0.clone(), fsetup.initial_offsets, fsetup.lb, fsetup.ub, fsetup.indiv_parts, out=fout, **fkw)
+
+            fstep()
+            ms_f = timed(fstep, args.steps)
+            extra["config4_fruitfly"] = {
+                "value": Cf * args.clip * args.steps / (ms_f * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_step": ms_f / args.steps,
+                "workload": f"fruitfly_force_free.xml (fly_treadmill cfg, {ftree.nbody} bodies, nq {ftree.nq}, {len(fsetup.site_idxs)} keypoints) synthetic "
+                            f"{Cf * args.clip}-frame session in {args.clip}-frame clips, sharded over {ws} GPU(s); general kernels",
+                "iters_per_frame": float(fout["iters"].sum().item()) / max((fhi - flo) * args.clip, 1) if fhi > flo else None,
+            }  # fmt: skip
+            del feng, fkp_dev, fout
+        except FileNotFoundError:
+            pass
     # ---------------- BASELINE config 3: full STAC fit (alternating m-phase / q-phase), clips sharded, m-phase all-reduced ----------------
     if not args.no_extras:
         fcfg = Cfg(cfg.to_dict())
