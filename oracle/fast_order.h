@@ -25,7 +25,8 @@
 #define IDL 31
 
 typedef struct {
-  int JM, RT, n, K, has_free, free_e, free_adr;
+  int JM, RT, n, K, has_free, free_e, free_adr, folded;
+  v3 srel_p[LANES]; q4 srel_q[LANES];    /* folded models: pose of the site's own body in its element's frame */
   q4 Qc[LANES], Qs[LANES];
   v3 A[LANES], B[LANES], C[LANES], anc0[LANES], ax0[LANES];
   v3 jax[LANES][FJ], jpp[LANES][FJ], jcx[LANES][FJ], jps[LANES][FJ];
@@ -90,40 +91,85 @@ static inline q4 f_normalize4(q4 q, REAL *rinv_out) {
 
 static void fast_destroy(ofast *F) { if (F) { free(F->passive); free(F); } }
 
-/* NULL when the register-resident path does not serve the model (mirrors stacb_tree_create / fits_fast) */
+/* pose of body b in the frame of its ancestor `top` (0 = world): constant transforms composed from the top down
+ * (mirrors rel_pose of csrc/stacb_abi.cu operation for operation) */
+static void f_rel_pose(const omodel *m, int top, int b, v3 *pos, q4 *quat) {
+  int chain[512], n = 0;
+  for (int c = b; c != top; c = m->body_parent[c]) chain[n++] = c;
+  pos->x = pos->y = pos->z = R(0); quat->w = R(1); quat->x = quat->y = quat->z = R(0);
+  for (int i = n - 1; i >= 0; i--) {
+    int c = chain[i];
+    if (i == n - 1) { *pos = ld3(m->body_pos + 3 * c); *quat = ld4(m->body_quat + 4 * c); }
+    else {
+      *pos = add3(*pos, f_rotq(ld3(m->body_pos + 3 * c), *quat));
+      *quat = c_qmul(*quat, ld4(m->body_quat + 4 * c));
+    }
+  }
+}
+
+/* NULL when the register-resident path does not serve the model (mirrors stacb_tree_create / fits_fast).
+ * Elements = the active bodies when they fit a warp; otherwise the JOINTED active bodies, every jointless (welded) active body
+ * folded into its nearest jointed ancestor with a constant relative pose (fruitfly). */
 static ofast *fast_create(const omodel *m, const osched *s) {
   int nb = m->nbody, K = m->nsite;
-  if (s->nact > 31 || K > 31) return NULL;
-  int *loc = (int *)calloc(nb, sizeof(int));
+  if (K > 31 || nb > 512) return NULL;
+  int fold = s->nact > 31;
+  int *loc = (int *)calloc(nb, sizeof(int)), *el = (int *)calloc(nb, sizeof(int)), *epar = (int *)calloc(nb, sizeof(int)), *edep = (int *)calloc(nb, sizeof(int));
+  int n_el = 0;
   for (int b = 0; b < nb; b++) loc[b] = -1;
-  for (int e = 0; e < s->nact; e++) loc[s->act[e]] = e;
-  int free_e = -1, free_j = -1, any_other = 0, jm = 1;
-  for (int e = 0; e < s->nact; e++) {
+  for (int e = 0; e < s->nact; e++) { int b = s->act[e]; if (!fold || m->body_jntnum[b] > 0) { loc[b] = n_el; el[n_el++] = b; } }
+#define OWNER(bb, out) { int q_ = (bb); while (q_ != 0 && loc[q_] < 0) q_ = m->body_parent[q_]; (out) = q_; }
+  int free_e = -1, free_j = -1, any_other = 0, jm = 1, maxd = 1;
+  for (int e = 0; e < s->nact; e++) {  /* joint census over ALL active bodies, as the library does */
     int b = s->act[e];
     if (m->body_jntnum[b] > jm) jm = m->body_jntnum[b];
     for (int jj = 0; jj < m->body_jntnum[b]; jj++) {
       int j = m->body_jntadr[b] + jj, t = m->jnt_type[j];
-      if (t == JNT_FREE && free_e < 0 && jj == 0) { free_e = e; free_j = j; }
+      if (t == JNT_FREE && free_e < 0 && jj == 0) { free_e = loc[b]; free_j = j; }
       else if (t != JNT_HINGE) any_other = 1;
     }
   }
+  for (int e = 0; e < n_el; e++) {
+    int pb; OWNER(m->body_parent[el[e]], pb);
+    epar[e] = pb != 0 ? loc[pb] : -1;
+    edep[e] = epar[e] >= 0 ? edep[epar[e]] + 1 : 1;
+    if (edep[e] > maxd) maxd = edep[e];
+  }
+  int rounds = ceil_log2(maxd);
   int nquat = 0;
   for (int j = 0; j < m->njnt; j++) if (m->jnt_type[j] == JNT_FREE || m->jnt_type[j] == JNT_BALL) nquat++;
   int JM = 0, RT = 0, bplf = (s->nfull + 31) / 32;
-  if (jm <= 1 && s->rounds_act <= 5 && bplf <= 1) { JM = 1; RT = 5; }
-  else if (jm <= 3 && s->rounds_act <= 4 && bplf <= 3) { JM = 3; RT = 4; }
-  if (any_other || nquat != (free_e >= 0 ? 1 : 0) || JM == 0) { free(loc); return NULL; }
+  if (jm <= 1 && rounds <= 5 && bplf <= 1) { JM = 1; RT = 5; }
+  else if (jm <= 2 && rounds <= 4 && bplf <= 3) { JM = 2; RT = 4; }
+  else if (jm <= 3 && rounds <= 4 && bplf <= 3) { JM = 3; RT = 4; }
+  int site_ok = 1;
+  for (int k = 0; k < K; k++) { int ob; OWNER(m->site_body[k], ob); if (ob == 0) site_ok = 0; }
+  if (n_el > 31 || n_el < 1 || any_other || nquat != (free_j >= 0 ? 1 : 0) || (free_j >= 0 && free_e < 0) || JM == 0 || !site_ok) {
+    free(loc); free(el); free(epar); free(edep);
+    return NULL;
+  }
+  /* ancestor tables of the element tree */
+  int nr = rounds > 0 ? rounds : 1;
+  int *eanc = (int *)calloc((size_t)nr * n_el, sizeof(int));
+  for (int e = 0; e < n_el; e++) eanc[e] = epar[e];
+  for (int r = 1; r < nr; r++)
+    for (int e = 0; e < n_el; e++) { int a = eanc[(size_t)(r - 1) * n_el + e]; eanc[(size_t)r * n_el + e] = a >= 0 ? eanc[(size_t)(r - 1) * n_el + a] : -1; }
   ofast *F = (ofast *)calloc(1, sizeof(ofast));
-  F->JM = JM; F->RT = RT; F->n = s->nact; F->K = K; F->has_free = free_e >= 0;
+  F->JM = JM; F->RT = RT; F->n = n_el; F->K = K; F->has_free = free_e >= 0;
   F->free_adr = free_e >= 0 ? m->jnt_qposadr[free_j] : 0;
   F->free_e = free_e >= 0 ? free_e : 0;
+  F->folded = fold;
   char *covered = (char *)calloc(m->nq + 1, 1);
   for (int l = 0; l < LANES; l++) {
-    int on = l < s->nact, b = on ? s->act[l] : 0;
+    int on = l < n_el, b = on ? el[l] : 0;
     v3 bpos = { 0, 0, 0 }; q4 bquat = { 1, 0, 0, 0 };
     int nj = 0;
-    if (on) { bpos = ld3(m->body_pos + 3 * b); bquat = ld4(m->body_quat + 4 * b); nj = m->body_jntnum[b]; }
-    F->pfree[l] = on && l == free_e;
+    if (on) {
+      nj = m->body_jntnum[b];
+      if (fold) { int pb; OWNER(m->body_parent[b], pb); f_rel_pose(m, pb, b, &bpos, &bquat); }
+      else { bpos = ld3(m->body_pos + 3 * b); bquat = ld4(m->body_quat + 4 * b); }
+    }
+    F->pfree[l] = on && free_e >= 0 && l == free_e;
     v3 a0 = { 0, 0, 0 }, p0 = { 0, 0, 0 };
     for (int jj = 0; jj < JM; jj++) {
       int j = on && jj < nj ? m->body_jntadr[b] + jj : -1;
@@ -153,21 +199,28 @@ static ofast *fast_create(const omodel *m, const osched *s) {
     F->anc0[l] = add3(f_rotq(p0, bquat), bpos);
     F->ax0[l] = f_rotq(a0, bquat);
     for (int r = 0; r < RT; r++) {
-      int a = l >= s->nact ? l : IDL;
-      if (on && r < s->rounds_act) { int t = s->anc[(size_t)r * nb + b]; if (t >= 0) a = loc[t]; }
+      int a = l >= n_el ? l : IDL;
+      if (on && r < rounds) { int t = eanc[(size_t)r * n_el + l]; if (t >= 0) a = t; }
       F->src[l][r] = a;
     }
-    int p = on ? m->body_parent[b] : 0;
-    F->par[l] = on ? (p != 0 ? loc[p] : IDL) : l;
+    F->par[l] = on ? (epar[l] >= 0 ? epar[l] : IDL) : l;
     int j0 = on && nj > 0 ? m->body_jntadr[b] : -1;
     int live = j0 >= 0 && s->jnt_e[j0] > s->jnt_s[j0];
     F->sa[l] = live ? s->jnt_s[j0] : 0; F->se[l] = live ? s->jnt_e[j0] : 0;
     F->sk[l] = -1; F->seb[l] = IDL;
-    if (l >= 1 && l <= K) { F->sk[l] = s->site_order[l - 1]; F->seb[l] = loc[m->site_body[s->site_order[l - 1]]]; }  /* site p on lane p + 1 */
+    F->srel_p[l].x = F->srel_p[l].y = F->srel_p[l].z = R(0);
+    F->srel_q[l].w = R(1); F->srel_q[l].x = F->srel_q[l].y = F->srel_q[l].z = R(0);
+    if (l >= 1 && l <= K) {  /* site p on lane p + 1 */
+      int k = s->site_order[l - 1], ob;
+      OWNER(m->site_body[k], ob);
+      F->sk[l] = k; F->seb[l] = loc[ob];
+      if (fold) f_rel_pose(m, ob, m->site_body[k], &F->srel_p[l], &F->srel_q[l]);
+    }
   }
+#undef OWNER
   F->passive = (int *)calloc(m->nq + 1, sizeof(int));
   for (int i = 0; i < m->nq; i++) if (!covered[i]) F->passive[F->npassive++] = i;
-  free(covered); free(loc);
+  free(covered); free(loc); free(el); free(epar); free(edep); free(eanc);
   if (F->npassive > 0 && F->passive[0] < 3) { fast_destroy(F); return NULL; }
   return F;
 }
@@ -188,6 +241,7 @@ static void fast_sites(const ofast *F, const REAL *site_pos, const REAL *kp, con
     int k = F->sk[l];
     if (k < 0) continue;
     if (site_pos) st->off[l] = ld3(site_pos + 3 * k);
+    if (F->folded) st->off[l] = add3(F->srel_p[l], f_rotq(st->off[l], F->srel_q[l]));
     if (kp) st->kp[l] = ld3(kp + 3 * k);
     if (kpmask) st->km[l] = ld3(kpmask + 3 * k);
   }

@@ -65,6 +65,7 @@ struct stacb_tree {
   DevTree T;
   int cpl, bpl_act, bpl_full, jm_act;
   bool fast_ok = false;                  // the register-resident hinge-tree solver applies (stacb_fast.cuh)
+  int fast_rounds = 0;                   // pointer-jumping rounds of its element set
   std::atomic<int> mode{-1};             // scheduling override of stacb_pose_clips (stacb_tree_set_mode)
   std::atomic<int> path{0};              // 0 = register-resident solver where it applies, 1 = general kernels only
   std::vector<void *> allocs;
@@ -134,6 +135,109 @@ static void build_set(const stacb_tree_desc &m, const std::vector<int> &set, con
       const int a = anc[(size_t)(r - 1) * n + e];
       anc[(size_t)r * n + e] = (a >= 0) ? anc[(size_t)(r - 1) * n + a] : -1;
     }
+}
+
+// ---- folding of jointless (welded) active bodies into their nearest jointed ancestor: float32 helpers written with explicit fused
+// multiply-adds in the operation order the CPU oracle uses for the same folding, so both sides derive identical constants ----
+static void h_cross(const float *a, const float *b, float *r) {
+  r[0] = fmaf(a[1], b[2], -(a[2] * b[1])); r[1] = fmaf(a[2], b[0], -(a[0] * b[2])); r[2] = fmaf(a[0], b[1], -(a[1] * b[0]));
+}
+static void h_rotq(const float *v, const float *q /*w,x,y,z*/, float *out) {
+  float t[3], c[3];
+  h_cross(q + 1, v, t);
+  h_cross(q + 1, t, c);
+  for (int i = 0; i < 3; i++) out[i] = fmaf(2.0f, fmaf(q[0], t[i], c[i]), v[i]);
+}
+static void h_qmul(const float *u, const float *v, float *r) {
+  r[0] = fmaf(-u[3], v[3], fmaf(-u[2], v[2], fmaf(-u[1], v[1], u[0] * v[0])));
+  r[1] = fmaf(-u[3], v[2], fmaf(u[2], v[3], fmaf(u[1], v[0], u[0] * v[1])));
+  r[2] = fmaf(u[3], v[1], fmaf(u[2], v[0], fmaf(-u[1], v[3], u[0] * v[2])));
+  r[3] = fmaf(u[3], v[0], fmaf(-u[2], v[1], fmaf(u[1], v[2], u[0] * v[3])));
+}
+// pose of body `b` in the frame of its ancestor `top` (0 = world): constant transforms composed from the top down
+static void rel_pose(const stacb_tree_desc &m, int top, int b, float *pos, float *quat) {
+  std::vector<int> chain;
+  for (int c = b; c != top; c = m.body_parent[c]) chain.push_back(c);
+  pos[0] = pos[1] = pos[2] = 0.f; quat[0] = 1.f; quat[1] = quat[2] = quat[3] = 0.f;
+  bool first = true;
+  for (int i = (int)chain.size() - 1; i >= 0; i--) {
+    const int c = chain[i];
+    if (first) {
+      for (int k = 0; k < 3; k++) pos[k] = m.body_pos[3 * c + k];
+      for (int k = 0; k < 4; k++) quat[k] = m.body_quat[4 * c + k];
+      first = false;
+    } else {
+      float r[3], q2[4];
+      h_rotq(m.body_pos + 3 * c, quat, r);
+      for (int k = 0; k < 3; k++) pos[k] = pos[k] + r[k];
+      h_qmul(quat, m.body_quat + 4 * c, q2);
+      for (int k = 0; k < 4; k++) quat[k] = q2[k];
+    }
+  }
+}
+
+// Element set with the jointless active bodies folded away.  Returns false when a keypoint site has no jointed ancestor-or-self.
+static bool build_folded_set(const stacb_tree_desc &m, const std::vector<int> &act, const std::vector<int> &subsize, const std::vector<int> &order,
+                             std::vector<int> &rec, std::vector<int> &anc, int &rounds, std::vector<int> &site_el, std::vector<float> &site_rel,
+                             int &n_el) {
+  const int K = m.nsite;
+  std::vector<int> el;  // element -> body
+  std::vector<int> loc(m.nbody, -1);
+  for (int b : act)
+    if (m.body_jntnum[b] > 0) { loc[b] = (int)el.size(); el.push_back(b); }
+  n_el = (int)el.size();
+  auto owner = [&](int b) { while (b != 0 && loc[b] < 0) b = m.body_parent[b]; return b; };  // nearest jointed ancestor-or-self (0: none)
+  std::vector<int> edepth(n_el, 1);
+  rec.assign((size_t)std::max(n_el, 1) * REC, 0);
+  int maxd = 1;
+  for (int e = 0; e < n_el; e++) {
+    const int b = el[e];
+    const int pb = owner(m.body_parent[b]);
+    int *r = rec.data() + (size_t)e * REC;
+    float pos[3], quat[4];
+    rel_pose(m, pb, b, pos, quat);
+    for (int c = 0; c < 3; c++) r[R_POS + c] = f2i(pos[c]);
+    for (int c = 0; c < 4; c++) r[R_QUAT + c] = f2i(quat[c]);
+    r[R_NJNT] = m.body_jntnum[b];
+    r[R_PARENT] = pb != 0 ? loc[pb] : -1;
+    r[R_BODY] = b;
+    edepth[e] = pb != 0 ? edepth[loc[pb]] + 1 : 1;
+    maxd = std::max(maxd, edepth[e]);
+    for (int jj = 0; jj < m.body_jntnum[b]; jj++) {
+      const int j = m.body_jntadr[b] + jj;
+      int *jr = r + R_JNT + J_STRIDE * jj;
+      jr[J_TYPE] = m.jnt_type[j];
+      jr[J_ADR] = m.jnt_qposadr[j];
+      for (int c = 0; c < 3; c++) { jr[J_POS + c] = f2i(m.jnt_pos[3 * j + c]); jr[J_AXIS + c] = f2i(m.jnt_axis[3 * j + c]); }
+      const int t = m.jnt_type[j];
+      jr[J_REF] = f2i((t == STACB_JNT_HINGE || t == STACB_JNT_SLIDE) ? m.qpos0[m.jnt_qposadr[j]] : 0.f);
+      const int lo = b, hi = b + subsize[b];
+      int a = 0;
+      while (a < K && m.site_body[order[a]] < lo) a++;
+      int e2 = a;
+      while (e2 < K && m.site_body[order[e2]] < hi) e2++;
+      jr[J_SA] = a;
+      jr[J_SE] = e2;
+    }
+  }
+  rounds = ceil_log2(maxd);
+  const int nr = std::max(rounds, 1);
+  anc.assign((size_t)nr * std::max(n_el, 1), -1);
+  for (int e = 0; e < n_el; e++) anc[e] = rec[(size_t)e * REC + R_PARENT];
+  for (int r = 1; r < nr; r++)
+    for (int e = 0; e < n_el; e++) {
+      const int a = anc[(size_t)(r - 1) * n_el + e];
+      anc[(size_t)r * n_el + e] = (a >= 0) ? anc[(size_t)(r - 1) * n_el + a] : -1;
+    }
+  site_el.assign(K, 0);
+  site_rel.assign((size_t)K * 7, 0.f);
+  for (int p = 0; p < K; p++) {
+    const int sb = m.site_body[order[p]], ob = owner(sb);
+    if (ob == 0) return false;
+    site_el[p] = loc[ob];
+    rel_pose(m, ob, sb, site_rel.data() + 7 * p, site_rel.data() + 7 * p + 3);
+  }
+  return true;
 }
 
 extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tree **out) {
@@ -240,7 +344,32 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
       stacb_tree_destroy(t);
       return rc;
     }
-    t->fast_ok = T.act.n <= 31 && K <= 31 && !T.any_other && T.nquat == (T.free_e >= 0 ? 1 : 0) && (passive.empty() || passive[0] >= 3);
+    // element set: the active bodies themselves when they fit a warp (rodent, C. elegans: records shared with the general path),
+    // otherwise the jointed active bodies with the welded ones folded in (fruitfly: 49-57 active bodies, 25 of them jointed)
+    T.fs = T.act; T.fs_free_e = T.free_e; T.site_efs = T.site_eact; T.site_rel = nullptr;
+    t->fast_rounds = T.act.rounds;
+    bool fits_warp = T.act.n <= 31;
+    if (!fits_warp) {
+      std::vector<int> rec_e, anc_e, site_el;
+      std::vector<float> site_rel;
+      int re = 0, n_el = 0;
+      if (build_folded_set(m, act, subsize, order, rec_e, anc_e, re, site_el, site_rel, n_el) && n_el <= 31 && n_el >= 1 && re <= RMAX) {
+        T.fs.n = n_el; T.fs.rounds = re;
+        const float *rel_dev = nullptr;
+        if ((rc = upload(t, rec_e, &T.fs.rec)) || (rc = upload(t, anc_e, &T.fs.anc)) || (rc = upload(t, site_el, &T.site_efs)) ||
+            (rc = upload(t, site_rel, &rel_dev))) {
+          stacb_tree_destroy(t);
+          return rc;
+        }
+        T.site_rel = rel_dev;
+        T.fs_free_e = -1;
+        for (int e = 0; e < n_el; e++)
+          if (rec_e[(size_t)e * REC + R_BODY] == (T.free_e >= 0 ? rec_a[(size_t)T.free_e * REC + R_BODY] : -1)) T.fs_free_e = e;
+        t->fast_rounds = re;
+        fits_warp = T.free_e < 0 || T.fs_free_e >= 0;
+      }
+    }
+    t->fast_ok = fits_warp && K <= 31 && !T.any_other && T.nquat == (T.free_e >= 0 ? 1 : 0) && (passive.empty() || passive[0] >= 3);
   }
   void *cnt = nullptr;
   if (cudaMalloc(&cnt, kCounterPool * sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
@@ -273,7 +402,7 @@ STACB_FAST_VARIANTS(X)
 }  // namespace stacb
 
 static bool fits_fast(const stacb_tree *t, int jm, int rt, int nbf) {
-  return t->fast_ok && t->path.load() == 0 && t->jm_act <= jm && t->T.act.rounds <= rt && t->bpl_full <= nbf;
+  return t->fast_ok && t->path.load() == 0 && t->jm_act <= jm && t->fast_rounds <= rt && t->bpl_full <= nbf;
 }
 
 static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl, int jm) {

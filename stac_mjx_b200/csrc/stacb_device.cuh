@@ -47,6 +47,12 @@ struct DevTree {
   const int *quat_adr;    // [nquat] qpos address of each quaternion
   int npassive;           // register-resident path (stacb_fast.cuh): qpos addresses outside its solver slots
   const int *passive;     // [npassive] ascending
+  // element set of the register-resident path: the active bodies, or -- when those do not fit a warp -- the active bodies that
+  // carry joints, every jointless (welded) active body folded into its nearest jointed ancestor with a constant relative pose
+  DevSet fs;
+  int fs_free_e;          // element of the primary free joint (-1 if none)
+  const int *site_efs;    // [K] by sorted position: element the site rides on
+  const float *site_rel;  // [K][7] by sorted position: pose (pos, quat) of the site's own body in that element's frame; null when nothing was folded
 };
 
 __host__ __device__ inline int role_smem_floats(const DevTree &T) { return 2 * T.nqp + 7 * T.pqn; }  // qbuf, gbuf, PQ

@@ -76,12 +76,12 @@ struct Fwd {
 
 template <int JM, int RT>
 __device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, int lane) {
-  const DevSet &S = T.act;
+  const DevSet &S = T.fs;
   const bool on = lane < S.n;
   BodyConst b;
   load_body(b, S.rec + (size_t)(on ? lane : 0) * REC);
   if (!on) { b.nj = 0; b.parent = -1; b.pos = mk3(0.f, 0.f, 0.f); b.quat = mk4(1.f, 0.f, 0.f, 0.f); }
-  L.pfree = on && lane == T.free_e;
+  L.pfree = on && lane == T.fs_free_e;
   V3 a0 = mk3(0.f, 0.f, 0.f), p0 = mk3(0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < JM; j++) {
@@ -124,9 +124,13 @@ __device__ __forceinline__ void site_init(SiteC &st, const DevTree &T, int lane,
   st.off = mk3(0.f, 0.f, 0.f); st.kp = mk3(0.f, 0.f, 0.f); st.km = mk3(0.f, 0.f, 0.f);
   if (lane >= 1 && lane <= T.K) {
     st.k = __ldg(T.site_order + lane - 1);
-    st.eb = __ldg(T.site_eact + lane - 1);
+    st.eb = __ldg(T.site_efs + lane - 1);
     st.ef = __ldg(T.site_efull + lane - 1);
     if (site_pos) st.off = mk3(__ldg(site_pos + 3 * st.k), __ldg(site_pos + 3 * st.k + 1), __ldg(site_pos + 3 * st.k + 2));
+    if (T.site_rel) {  // the site's body is welded to the element: express the offset in the element's frame (uniform branch)
+      const float *r = T.site_rel + 7 * (lane - 1);
+      st.off = add3(mk3(__ldg(r), __ldg(r + 1), __ldg(r + 2)), rotq(st.off, mk4(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5), __ldg(r + 6))));
+    }
   }
 }
 __device__ __forceinline__ void site_load_kp(SiteC &st, const float *__restrict__ kp) {
@@ -664,7 +668,7 @@ __device__ __forceinline__ void slots_init(Slots<JM + 1> &co, SlotAdr<JM> &sa, c
                                            const float *__restrict__ lb, const float *__restrict__ ub) {
 #pragma unroll
   for (int j = 0; j < JM; j++) { co.valid[j] = L.hinge[j]; sa.adr[j] = L.adr[j]; }
-  co.valid[JM] = T.free_e >= 0 && lane < 7;
+  co.valid[JM] = T.fs_free_e >= 0 && lane < 7;
   sa.adr[JM] = co.valid[JM] ? T.free_adr + lane : 0;
 #pragma unroll
   for (int m = 0; m <= JM; m++) {
@@ -729,7 +733,8 @@ __device__ __forceinline__ void normalize_free(const Uni &u, float (&q)[JM + 1])
 
 // Full-model FK of the qpos vector in ch.qbuf (normalised in place) and the per-frame outputs: the general cold path.
 template <int NBF>
-__device__ __forceinline__ void outputs_from_qbuf(const Chain &ch, const SiteC &st, float *qpos_o, float *xpos_o, float *xquat_o, float *sites_o) {
+__device__ __forceinline__ void outputs_from_qbuf(const Chain &ch, const SiteC &st, const float *__restrict__ site_pos, float *qpos_o, float *xpos_o,
+                                                  float *xquat_o, float *sites_o) {
   V3 P[NBF];
   Q4 Q[NBF];
   fk_cold<NBF>(ch, ch.T.full, P, Q);
@@ -749,9 +754,10 @@ __device__ __forceinline__ void outputs_from_qbuf(const Chain &ch, const SiteC &
     if (xpos_o) { xpos_o[0] = 0.f; xpos_o[1] = 0.f; xpos_o[2] = 0.f; }
     if (xquat_o) { xquat_o[0] = 1.f; xquat_o[1] = 0.f; xquat_o[2] = 0.f; xquat_o[3] = 0.f; }
   }
-  if (sites_o && st.k >= 0) {
+  if (sites_o && st.k >= 0) {  // the site's own body and its original offset (st.off may be expressed in an element's frame)
     const float *o = ch.PQ + 7 * st.ef;
-    const V3 s = add3(lds3(o), rotate(st.off, lds4(o + 3)));
+    const V3 off = mk3(__ldg(site_pos + 3 * st.k), __ldg(site_pos + 3 * st.k + 1), __ldg(site_pos + 3 * st.k + 2));
+    const V3 s = add3(lds3(o), rotate(off, lds4(o + 3)));
     sites_o[3 * st.k] = s.x; sites_o[3 * st.k + 1] = s.y; sites_o[3 * st.k + 2] = s.z;
   }
   __syncwarp();
@@ -787,7 +793,7 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
   SlotAdr<JM> sa;
   slots_init<JM, RT>(co, sa, L, T, lane, a.lb, a.ub);
   Uni u;
-  u.lane = lane; u.free_e = T.free_e >= 0 ? T.free_e : 0; u.has_free = T.free_e >= 0;
+  u.lane = lane; u.free_e = T.fs_free_e >= 0 ? T.fs_free_e : 0; u.has_free = T.fs_free_e >= 0;
   u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls; u.betas = s_beta;
   const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P, npassive = T.npassive;
   const MaskSpec full_ms = {nullptr, nq}, root_ms = {nullptr, a.root_dims};
@@ -860,7 +866,7 @@ __global__ void __launch_bounds__(NC ? 64 * NC : 128, MINB) fast_pose_kernel(Dev
         if (sg == a.P && writer) {  // last solve of the frame: full-model FK of the raw solution -> outputs
           slots_scatter<JM>(co, sa, q, ch.qbuf);
           __syncwarp();
-          outputs_from_qbuf<NBF>(ch, st, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
+          outputs_from_qbuf<NBF>(ch, st, a.site_pos, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
                                  a.xquat ? a.xquat + fi * nb * 4 : nullptr, a.sites ? a.sites + fi * K * 3 : nullptr);
           if (a.err && lane == 0) a.err[fi] = so.err;
         }
@@ -896,7 +902,7 @@ __global__ void __launch_bounds__(128) fast_batch_kernel(DevTree T, BatchArgs a)
   SlotAdr<JM> sa;
   slots_init<JM, RT>(co, sa, L, T, lane, a.lb, a.ub);
   Uni u;
-  u.lane = lane; u.free_e = T.free_e >= 0 ? T.free_e : 0; u.has_free = T.free_e >= 0;
+  u.lane = lane; u.free_e = T.fs_free_e >= 0 ? T.fs_free_e : 0; u.has_free = T.fs_free_e >= 0;
   u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls; u.betas = s_beta;
   const int nq = T.nq, K = T.K;
   const MaskSpec ms = {a.q_mask, nq};

@@ -169,7 +169,7 @@ def test_oracle_reproduces_golden_vectors(name):
     kw = c.root_kw()
     C, F = g["c32_clip_qpos"].shape[:2]
     fast = c.oracle(np.float32, 2).fast_path
-    assert fast == ("g32_clip_qpos" in g.files) == (name in ("rodent", "celegans", "synth_data"))
+    assert fast == ("g32_clip_qpos" in g.files) == (name in ("rodent", "celegans", "synth_data", "fly_treadmill"))
     for tag, mode in (("c32", 1),) + ((("g32", 2),) if fast else ()):
         o = c.oracle(np.float32, mode)
         r = o.pose_clips(g["kp"].reshape(C, F, -1), c.tree.qpos0, g["offsets"], c.setup.lb, c.setup.ub, c.setup.indiv_parts, nthreads=4, **kw)
@@ -224,7 +224,7 @@ def test_mode0_solver_output_is_frozen(rodent):
         np.testing.assert_allclose(r["qpos"][0], g[f"{tag}_qpos"][:n], atol=tol, rtol=0)
 
 
-@pytest.mark.parametrize("name", ["rodent", "celegans", "synth_data"])
+@pytest.mark.parametrize("name", ["rodent", "celegans", "synth_data", "fly_treadmill"])
 def test_fast_order_agrees_with_mjx_order(name):
     """mode 2 (register-resident kernel arithmetic) vs mode 0: the same mathematics -- to 1e-12 in float64, to float32
     rounding in float32 -- including the analytic gradient against reverse-mode autodiff and a solve that starts with
@@ -237,21 +237,25 @@ def test_fast_order_agrees_with_mjx_order(name):
     np.testing.assert_allclose(g["g32_mgrad"], g["f64_mgrad"], atol=3e-5 * max(np.abs(g["f64_mgrad"]).max(), 1e-9))
     o0, o2 = c.oracle(np.float64, 0), c.oracle(np.float64, 2)
     assert o2.fast_path
+    # float64 agreement: 1e-12 where the model's body quaternions are exactly unit in float32; the fruitfly's are unit only to
+    # float32 rounding, and MJX's rotate() scales by |q|^2 where the fast order's rotq() does not (a 1e-7 relative difference in
+    # the MODEL, far below every tolerance of the path)
+    ftol = 1e-12 if name != "fly_treadmill" else 1e-6
     T = TorchModel(c.tree, c.setup.site_bodies)
     for i in range(2):
         a = o0.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
         b = o2.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
         L, G = T.loss_grad(g["q"][i], g["q0"][i], g["qm_part"], g["kp"][i], g["km_trunk"], g["offsets"])
-        assert abs(float(a[0]) - float(b[0])) < 1e-12 * max(1.0, float(a[0])) and abs(float(b[0]) - L) < 1e-12 * max(1.0, L)
-        np.testing.assert_allclose(b[1], a[1], atol=1e-11 * max(1.0, np.abs(a[1]).max()))
-        np.testing.assert_allclose(b[1], G, atol=2e-8 * max(1.0, np.abs(G).max()))
+        assert abs(float(a[0]) - float(b[0])) < ftol * max(1.0, float(a[0])) and abs(float(b[0]) - L) < ftol * max(1.0, L)
+        np.testing.assert_allclose(b[1], a[1], atol=10 * ftol * max(1.0, np.abs(a[1]).max()))
+        np.testing.assert_allclose(b[1], G, atol=max(2e-8, ftol) * max(1.0, np.abs(G).max()))
     q0 = g["q0"][0].astype(np.float64).copy()
     q0[-1] = c.setup.ub[-1] + 0.5 if np.isfinite(c.setup.ub[-1]) else q0[-1]  # outside the box (a passive hinge for the rodent)
     qm, km = np.ones(c.tree.nq, bool), np.ones(3 * c.K, bool)
     r0 = o0.q_opt(q0, c.setup.lb, c.setup.ub, qm, g["kp"][0], km, g["offsets"], 1e-9, maxiter=25)
     r2 = o2.q_opt(q0, c.setup.lb, c.setup.ub, qm, g["kp"][0], km, g["offsets"], 1e-9, maxiter=25)
     assert (r0[2], r0[3]) == (r2[2], r2[3])
-    np.testing.assert_allclose(r2[0], r0[0], atol=1e-9)
+    np.testing.assert_allclose(r2[0], r0[0], atol=1e-9 if name != "fly_treadmill" else 1e-5)
 
 
 @pytest.mark.parametrize("name", ["rodent", "celegans", "fly_treadmill", "mouse"])
