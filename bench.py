@@ -329,7 +329,7 @@ def run_ours(args):
         }  # fmt: skip
         del B
         torch.cuda.empty_cache()
-    # ---------------- BASELINE config 4: fruitfly (deeper / wider tree: general kernels), one 18 000-frame session sharded by clip ----------------
+    # ---------------- BASELINE config 4: fruitfly (deeper / wider tree), one 18 000-frame session sharded by clip ----------------
     if not args.no_extras:
         try:
             ftree, fcfg4, fsetup = load_case("fly_treadmill")
@@ -351,7 +351,8 @@ def run_ours(args):
             extra["config4_fruitfly"] = {
                 "value": Cf * args.clip * args.steps / (ms_f * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_step": ms_f / args.steps,
                 "workload": f"fruitfly_force_free.xml (fly_treadmill cfg, {ftree.nbody} bodies, nq {ftree.nq}, {len(fsetup.site_idxs)} keypoints) synthetic "
-                            f"{Cf * args.clip}-frame session in {args.clip}-frame clips, sharded over {ws} GPU(s); general kernels",
+                            f"{Cf * args.clip}-frame session in {args.clip}-frame clips, sharded over {ws} GPU(s); "
+                            + ("register-resident kernels (welded bodies folded)" if feng.path else "general kernels"),
                 "iters_per_frame": float(fout["iters"].sum().item()) / max((fhi - flo) * args.clip, 1) if fhi > flo else None,
             }  # fmt: skip
             del feng, fkp_dev, fout

@@ -78,3 +78,29 @@ def test_jax_ffi_front_end_is_guarded():
     assert jax_ffi.available() is False
     with pytest.raises(RuntimeError, match="JAX FFI path unavailable"):
         jax_ffi.register()
+
+
+def test_tree_create_rejects_body_orders_that_are_not_depth_first():
+    """The gradient's subtree = contiguous site range logic needs DFS pre-order body ids (what MuJoCo produces): a merely
+    topological order (every parent before its children, but a subtree interleaved with a sibling) is refused -- before any
+    CUDA call, so this runs without a GPU."""
+    import ctypes as C
+
+    import numpy as np
+
+    from stac_mjx_b200 import _lib
+
+    L = _lib.lib()
+    nb = 5
+    parent = np.array([0, 0, 0, 1, 2], np.int32)  # body 3 hangs off body 1, but body 2 (a sibling subtree) sits in between
+    jadr = np.array([-1, 0, 1, 2, 3], np.int32)
+    jnum = np.array([0, 1, 1, 1, 1], np.int32)
+    pos, quat = np.zeros((nb, 3), np.float32), np.tile(np.array([1, 0, 0, 0], np.float32), (nb, 1))
+    jt, jq, jb = np.full(4, 3, np.int32), np.arange(4, dtype=np.int32), np.arange(1, 5, dtype=np.int32)
+    jp, ja = np.zeros((4, 3), np.float32), np.tile(np.array([0, 0, 1], np.float32), (4, 1))
+    q0, sb = np.zeros(4, np.float32), np.array([3, 4], np.int32)
+    keep = [parent, jadr, jnum, pos, quat, jt, jq, jb, jp, ja, q0, sb]
+    d = _lib.TreeDesc(nb, 4, 4, 2, *[a.ctypes.data_as(C.c_void_p) for a in keep])
+    h = C.c_void_p()
+    assert L.stacb_tree_create(C.byref(d), 0, C.byref(h)) == -1
+    assert b"depth-first pre-order" in L.stacb_last_error()

@@ -30,10 +30,19 @@ def quiet(fn, *a):
 stac = Stac(None, cfg, kpn, tree=tree, device=local)
 single_ik = quiet(stac.ik_only, kp, setup.initial_offsets)          # no process group yet: every rank runs all clips
 single_fit = quiet(stac.fit_offsets, kp[:F * 2])
+ccfg = Cfg(cfg.to_dict()); ccfg.stac.continuous = True              # overlapping clips + device epilogues (cross-fade, qvel)
+cstac = Stac(None, ccfg, kpn, tree=tree, device=local)
+single_c = quiet(lambda: cstac.ik_only(kp, setup.initial_offsets, edge_effects=True, infer_qvels=True))
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 multi_ik = quiet(stac.ik_only, kp, setup.initial_offsets)           # clips sharded over ranks, results all-gathered
 multi_fit = quiet(stac.fit_offsets, kp[:F * 2])                     # q-phase replicated, m-phase frames sharded + all-reduce
+multi_c = quiet(lambda: cstac.ik_only(kp, setup.initial_offsets, edge_effects=True, infer_qvels=True))
 ok = True
+for k in ("qpos", "xpos", "marker_sites", "qvel", "kp_data"):
+    same = np.array_equal(getattr(single_c, k), getattr(multi_c, k))
+    ok &= same
+    if rank == 0:
+        print(f"continuous ik_only + epilogues {k}: sharded == single-GPU bitwise: {same}")
 for k in ("qpos", "xpos", "xquat", "marker_sites"):
     same = np.array_equal(getattr(single_ik, k), getattr(multi_ik, k))
     ok &= same
