@@ -30,7 +30,7 @@ def quiet(fn, *a):
 stac = Stac(None, cfg, kpn, tree=tree, device=local)
 single_ik = quiet(stac.ik_only, kp, setup.initial_offsets)          # no process group yet: every rank runs all clips
 single_fit = quiet(stac.fit_offsets, kp[:F * 2])
-ccfg = Cfg(cfg.to_dict()); ccfg.stac.continuous = True              # overlapping clips + device epilogues (cross-fade, qvel)
+ccfg = Cfg(cfg.to_dict()); ccfg.stac.continuous = True; ccfg.stac.n_frames_per_clip = 10   # overlapping clips (4 x (10 + 10 look-ahead)) + device epilogues
 cstac = Stac(None, ccfg, kpn, tree=tree, device=local)
 single_c = quiet(lambda: cstac.ik_only(kp, setup.initial_offsets, edge_effects=True, infer_qvels=True))
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
