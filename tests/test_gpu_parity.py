@@ -524,3 +524,56 @@ def test_large_batches_use_the_multi_warp_cta_path(rodent, engine_of):
         po, eo, ito, lso = o.q_opt(q[i], s.lb, s.ub, qm, kp[i], km, s.initial_offsets, 1e-4, maxiter=5)
         np.testing.assert_array_equal(p[i], po)
         assert (it[i], ls[i]) == (ito, lso)
+
+
+@pytest.mark.parametrize("seed", [0, 2, 3, 5, 7, 8, 10, 11])
+def test_random_trees_with_welded_bodies_on_the_register_resident_path(seed):
+    """Random hinge trees with welded bodies (tests/random_trees.py): the library and the oracle must agree on WHETHER the
+    register-resident path serves the model (same folding, same variant choice) and then bit for bit on loss / gradient,
+    single solves (masked, with frozen coordinates outside their box) and clips in every scheduling mode."""
+    from oracle.oracle import Oracle
+    from random_trees import random_tree
+    from stac_mjx_b200.engine import Engine
+
+    t, site_idxs, lb, ub = random_tree(seed, n_bodies=40 + 3 * seed, p_welded=0.3 + 0.03 * seed, n_sites=min(31, 8 + 2 * seed))
+    sb, off = t.site_bodyid[site_idxs], t.site_pos[site_idxs].astype(np.float32)
+    K = len(sb)
+    eng, o = Engine(t, sb, 0), Oracle(t, sb, np.float32, 2)
+    assert eng.path == 1 and o.fast_path
+    rng = np.random.default_rng(seed)
+    q = (t.qpos0 + rng.normal(scale=0.2, size=(6, t.nq))).astype(np.float32)
+    q0 = (q + rng.normal(scale=0.05, size=q.shape)).astype(np.float32)
+    kp = np.stack([o.fk(q[(i + 1) % 6], off)[3].reshape(-1) for i in range(6)]).astype(np.float32) + 0.004
+    qm, km = np.ones(t.nq, bool), np.ones(3 * K, bool)
+    part = rng.random(t.nq) < 0.5
+    for mask in (qm, part):
+        L, G = [npy(x) for x in eng.loss_grad(q, q0, kp, mask, km, off)]
+        for i in range(6):
+            l, g = o.loss_grad(q[i], q0[i], mask, kp[i], km, off)
+            assert float(l) == float(L[i])
+            np.testing.assert_array_equal(G[i], g)
+    qs = q[:3].copy()
+    qs[:, 8:12] += 9.0  # frozen (masked-out) and optimised coordinates outside their boxes
+    p, e, it, ls = [npy(x) for x in eng.q_opt(qs, kp[:3], part, km, off, lb, ub, 1e-5, maxiter=40)]
+    for i in range(3):
+        po, eo, ito, lso = o.q_opt(qs[i], lb, ub, part, kp[i], km, off, 1e-5, maxiter=40)
+        assert (it[i], ls[i]) == (ito, lso)
+        np.testing.assert_array_equal(p[i], po)
+    kpc = kp.reshape(2, 3, -1)
+    kw = dict(do_root=1, root_kp_idx=0, trunk_kps=rng.random(K) < 0.7, tol=1e-5, maxiter=60)
+    kw["trunk_kps"][0] = True
+    ref = o.pose_clips(kpc, t.qpos0, off, lb, ub, part[None], **kw)
+    for mode in (0, 1, 2, 3, 4):
+        eng.set_mode(mode)
+        qio = torch.tensor(np.tile(t.qpos0.astype(np.float32), (2, 1)), device=eng.device)
+        out = eng.pose_clips(kpc, qio, off, lb, ub, part[None], **kw)
+        np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
+        for k in ("qpos", "xpos", "xquat", "sites", "err"):
+            np.testing.assert_array_equal(npy(out[k]), ref[k], err_msg=f"mode {mode} {k}")
+    # the general kernels on the same model agree to rounding
+    eng.set_mode(-1)
+    eng.set_path(1)
+    L1, G1 = [npy(x) for x in eng.loss_grad(q, q0, kp, qm, km, off)]
+    L0, G0 = [npy(x) for x in Engine(t, sb, 0).loss_grad(q, q0, kp, qm, km, off)]
+    np.testing.assert_allclose(L1, L0, rtol=2e-5)
+    np.testing.assert_allclose(G1, G0, atol=2e-5 * max(1.0, np.abs(G0).max()))

@@ -353,3 +353,36 @@ def test_all_joint_types_gradient_and_orders():
     f32 = Oracle(t, sb, np.float32, 1)
     p, e, it, ls = f32.q_opt(q[0], lb, ub, qm, kp, km, off, 1e-5, maxiter=60)
     assert it > 3 and np.isfinite(p).all()
+
+
+@pytest.mark.parametrize("seed", [0, 3, 6, 9, 11])
+def test_fast_order_on_random_trees_with_welded_bodies(seed):
+    """Random hinge trees (free root, 1-3 hinges per jointed body, 30-60 % welded bodies, sites on jointed and welded bodies):
+    the element folding of the register-resident path (oracle mode 2) computes the same loss and gradient as the MJX order
+    and as reverse-mode autodiff.  Body quaternions are unit to float32 rounding only, so float64 agreement is ~1e-7
+    relative (MJX's rotate() scales by |q|^2)."""
+    from random_trees import n_active, random_tree
+
+    t, site_idxs, lb, ub = random_tree(seed, n_bodies=40 + 3 * seed, p_welded=0.3 + 0.03 * seed, n_sites=min(31, 8 + 2 * seed))
+    sb, off = t.site_bodyid[site_idxs], t.site_pos[site_idxs]
+    na, nj = n_active(t, sb)
+    o0, o2 = Oracle(t, sb, np.float64, 0), Oracle(t, sb, np.float64, 2)
+    assert o2.fast_path and nj <= 31 and (seed < 3) == (na <= 31)  # seeds >= 3 need the folding
+    rng = np.random.default_rng(seed)
+    T = TorchModel(t, sb)
+    qm, km = np.ones(t.nq, bool), np.ones(3 * len(sb), bool)
+    part = rng.random(t.nq) < 0.5
+    for i in range(2):
+        q = t.qpos0 + rng.normal(scale=0.2, size=t.nq)
+        q0 = q + rng.normal(scale=0.05, size=t.nq)
+        kp = o0.fk(t.qpos0 + rng.normal(scale=0.2, size=t.nq), off)[3].reshape(-1) + 0.003
+        for mask in (qm, part):
+            a, b = o0.loss_grad(q, q0, mask, kp, km, off), o2.loss_grad(q, q0, mask, kp, km, off)
+            L, G = T.loss_grad(q, q0, mask, kp, km, off)
+            assert abs(float(a[0]) - float(b[0])) < 2e-6 * max(1e-3, float(a[0]))
+            np.testing.assert_allclose(b[1], a[1], atol=2e-6 * max(1.0, np.abs(a[1]).max()))
+            np.testing.assert_allclose(b[1], G, atol=2e-6 * max(1.0, np.abs(G).max()))
+            assert (b[1][~mask] == 0).all()
+    r0 = o0.q_opt(q, lb, ub, qm, kp, km, off, 1e-9, maxiter=15)
+    r2 = o2.q_opt(q, lb, ub, qm, kp, km, off, 1e-9, maxiter=15)
+    np.testing.assert_allclose(r2[0], r0[0], atol=2e-4)
