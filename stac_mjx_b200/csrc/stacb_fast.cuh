@@ -1,11 +1,13 @@
 // stacb_fast.cuh -- the register-resident solver for hinge trees (sm_100a): the hot path of libstacb.so.
 //
-// Applies to models whose ACTIVE subtree (ancestors of the marker bodies) has at most 31 bodies, at most 31 marker sites,
-// hinge joints only plus (optionally) one free joint on a top-level body: the rodent / rat23 and C. elegans models of the
-// reference.  Everything else takes the general kernels of stacb_device.cuh.
+// Applies to models whose ACTIVE subtree (ancestors of the marker bodies) reduces to at most 31 ELEMENTS and at most 31 marker
+// sites, with hinge joints only plus (optionally) one free joint on a top-level body.  Elements are the active bodies themselves
+// when they fit (rodent / rat23: 31, C. elegans: 25); otherwise the active bodies that carry joints, every jointless (welded) active
+// body folded into its nearest jointed ancestor by stacb_tree_create (fruitfly: 49-57 active bodies -> 25 elements).  Everything
+// else takes the general kernels of stacb_device.cuh.
 //
 // Mapping (fixed for the whole kernel, all state in registers, no shared memory inside an evaluation):
-//   lane e  <->  active body e (set order = body id order, parents first); lane 31 (and every lane >= n) is an IDENTITY
+//   lane e  <->  element e (body id order, parents first); lane 31 (and every lane >= n) is an IDENTITY
 //               element, so "no ancestor" needs no select: composing with the identity is exact;
 //   lane p+1 <-> marker site at sorted position p (sites sorted by body id, so a subtree is a contiguous range; lane 0 carries
 //               a zero wrench, which makes the inclusive prefix scan over the lanes the exclusive one of the sites);
@@ -46,7 +48,7 @@ template <int JM, int RT>
 struct LaneC {
   Q4 Qc, Qs;            // first hinge folded with the body's constant pose
   V3 A, B, C;
-  V3 anc[JM], ax[JM];   // slot 0: constant parent-frame anchor / axis of the first hinge (slots >= 1 live in Fwd)
+  V3 anc[JM], ax[JM];   // slot 0: constant parent-frame anchor / axis of the first hinge (slots >= 1 are derived in the reverse sweep)
   V3 jax[JM], jpp[JM], jcx[JM], jps[JM];  // slots >= 1: axis, jpos - a (a.jpos), a x jpos, jpos (body frame)
   float ref[JM];
   int adr[JM];          // qpos address of the hinge in slot j (0 when the slot is empty)
@@ -196,7 +198,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<JM, RT> &L, const SiteC &s
   return warp_sum(fmaf(S.res.z, S.res.z, fmaf(S.res.y, S.res.y, S.res.x * S.res.x)));
 }
 
-// Reverse half: d loss / d (solver slots) at the point of the last eval_fwd<KEEP = true>.
+// Reverse half: d loss / d (solver slots) at the point of the last eval_fwd (its state S is still live).
 //   free_wanted: some coordinate of the free joint is optimised (uniform); free_e: lane of the free joint's body.
 template <int JM, int RT>
 __device__ __forceinline__ void eval_bwd(const LaneC<JM, RT> &L, const Fwd<JM> &S, int lane, bool free_wanted, int free_e, float (&g)[JM + 1]) {
