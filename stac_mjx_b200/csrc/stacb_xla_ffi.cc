@@ -1,7 +1,9 @@
 // stacb_xla_ffi.cc -- XLA FFI handlers (typed FFI API, jaxlib >= 0.4.31) around the C ABI of include/stacb.h.
 //
-// NOT COMPILED IN THE AUTHORING IMAGE: jax / jaxlib (and therefore xla/ffi/api/ffi.h) are not installed there, so this
-// translation unit has never been through a compiler.  build.sh builds it into libstacb_xla_ffi.so only when
+// NOT BUILT IN THE AUTHORING IMAGE: jax / jaxlib (and therefore xla/ffi/api/ffi.h) are not installed there.  The translation unit is
+// type-checked (g++ -fsyntax-only) against a mock of the FFI API's shape (tests/xla_ffi_mock, tests/test_abi_cpu.py): every handler
+// matches its binding and every C ABI call matches include/stacb.h; it has never run inside XLA.  build.sh builds it into
+// libstacb_xla_ffi.so only when
 // `python -c "import jax.ffi; print(jax.ffi.include_dir())"` succeeds.  It contains no arithmetic: every handler unpacks
 // XLA buffers into the plain pointers of the C ABI and forwards the stream XLA hands it.  Python side: stac_mjx_b200/jax_ffi.py.
 //

@@ -104,3 +104,18 @@ def test_tree_create_rejects_body_orders_that_are_not_depth_first():
     h = C.c_void_p()
     assert L.stacb_tree_create(C.byref(d), 0, C.byref(h)) == -1
     assert b"depth-first pre-order" in L.stacb_last_error()
+
+
+def test_xla_ffi_handlers_type_check_against_a_mock_of_the_ffi_api():
+    """csrc/stacb_xla_ffi.cc cannot be built here (no jaxlib headers).  It is compiled (-fsyntax-only) against a mock with the shape
+    of xla/ffi/api/ffi.h: every handler must be invocable with exactly the argument list its binding declares, and every C ABI
+    call must match include/stacb.h -- so a change of the C ABI cannot silently rot the FFI layer."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-I", str(ROOT / "tests" / "xla_ffi_mock"), "-I", str(ROOT / "include"),
+           "-I", "/usr/local/cuda/include", str(ROOT / "stac_mjx_b200" / "csrc" / "stacb_xla_ffi.cc")]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
