@@ -22,19 +22,20 @@
 
 #define FJ 3 /* slots a variant can have */
 #define FNS (FJ + 1)
-#define IDL 31
+#define FMAXL 256 /* lanes of the widest variant: 8 warps */
 
 typedef struct {
   int JM, RT, n, K, has_free, free_e, free_adr, folded;
-  v3 srel_p[LANES]; q4 srel_q[LANES];    /* folded models: pose of the site's own body in its element's frame */
-  q4 Qc[LANES], Qs[LANES];
-  v3 A[LANES], B[LANES], C[LANES], anc0[LANES], ax0[LANES];
-  v3 jax[LANES][FJ], jpp[LANES][FJ], jcx[LANES][FJ], jps[LANES][FJ];
-  REAL ref[LANES][FJ];
-  int hinge[LANES][FJ], pfree[LANES];
-  int src[LANES][8], par[LANES], sa[LANES], se[LANES];
-  int sk[LANES], seb[LANES];             /* sites: keypoint index (-1 none), lane of the body */
-  int valid[LANES][FNS], adr[LANES][FNS]; /* solver slots */
+  int W, NL, idl;                        /* warps per evaluation, lanes = 32 W, identity lane = NL - 1 */
+  v3 srel_p[FMAXL]; q4 srel_q[FMAXL];    /* folded models: pose of the site's own body in its element's frame */
+  q4 Qc[FMAXL], Qs[FMAXL];
+  v3 A[FMAXL], B[FMAXL], C[FMAXL], anc0[FMAXL], ax0[FMAXL];
+  v3 jax[FMAXL][FJ], jpp[FMAXL][FJ], jcx[FMAXL][FJ], jps[FMAXL][FJ];
+  REAL ref[FMAXL][FJ];
+  int hinge[FMAXL][FJ], pfree[FMAXL];
+  int src[FMAXL][8], par[FMAXL], sa[FMAXL], se[FMAXL];
+  int sk[FMAXL], seb[FMAXL];             /* sites: keypoint index (-1 none), lane of the body */
+  int valid[FMAXL][FNS], adr[FMAXL][FNS]; /* solver slots */
   int npassive, *passive;
 } ofast;
 
@@ -45,6 +46,14 @@ static inline v3 f_rotq(v3 v, q4 q) {
   v3 w = { r_fma(q.w, t.x, c.x), r_fma(q.w, t.y, c.y), r_fma(q.w, t.z, c.z) };
   v3 r = { r_fma(R(2), w.x, v.x), r_fma(R(2), w.y, v.y), r_fma(R(2), w.z, v.z) };
   return r;
+}
+
+/* sum over the NL = 32 W lanes of an evaluation: the 32-lane butterfly inside every warp, then the warp sums added in warp order
+ * (W = 1: the butterfly alone) */
+static REAL f_cta_sum(int W, REAL *part) {
+  REAL tot = R(0);
+  for (int w = 0; w < W; w++) { REAL b = butterfly32(part + LANES * w); tot = (w == 0) ? b : tot + b; }
+  return tot;
 }
 
 /* (-1)^j (sin x, cos x), j = rint(x / pi): mirrors sincos_pi of csrc/stacb_math.cuh (the common sign cancels in FK) */
@@ -112,7 +121,7 @@ static void f_rel_pose(const omodel *m, int top, int b, v3 *pos, q4 *quat) {
  * folded into its nearest jointed ancestor with a constant relative pose (fruitfly). */
 static ofast *fast_create(const omodel *m, const osched *s) {
   int nb = m->nbody, K = m->nsite;
-  if (K > 31 || nb > 512) return NULL;
+  if (nb > 512) return NULL;
   int fold = s->nact > 31;
   int *loc = (int *)calloc(nb, sizeof(int)), *el = (int *)calloc(nb, sizeof(int)), *epar = (int *)calloc(nb, sizeof(int)), *edep = (int *)calloc(nb, sizeof(int));
   int n_el = 0;
@@ -138,13 +147,19 @@ static ofast *fast_create(const omodel *m, const osched *s) {
   int rounds = ceil_log2(maxd);
   int nquat = 0;
   for (int j = 0; j < m->njnt; j++) if (m->jnt_type[j] == JNT_FREE || m->jnt_type[j] == JNT_BALL) nquat++;
-  int JM = 0, RT = 0, bplf = (s->nfull + 31) / 32;
-  if (jm <= 1 && rounds <= 5 && bplf <= 1) { JM = 1; RT = 5; }
-  else if (jm <= 2 && rounds <= 4 && bplf <= 3) { JM = 2; RT = 4; }
-  else if (jm <= 3 && rounds <= 4 && bplf <= 3) { JM = 3; RT = 4; }
+  int JM = 0, RT = 0, bplf = (s->nfull + 31) / 32, W = 1;
+  if (n_el <= 31) {  /* one warp: the kernel variant is the first fit, surplus slots / rounds are executed as no-ops */
+    if (jm <= 1 && rounds <= 5 && bplf <= 1) { JM = 1; RT = 5; }
+    else if (jm <= 2 && rounds <= 4 && bplf <= 3) { JM = 2; RT = 4; }
+    else if (jm <= 3 && rounds <= 4 && bplf <= 3) { JM = 3; RT = 4; }
+    if (K > 31) JM = 0;
+  } else {           /* wide variant: W = 2, 4, 6 or 8 warps per evaluation, one hinge per element, exact round count */
+    W = 2 * ((n_el + 1 + 63) / 64);
+    if (W <= 8 && jm <= 1 && rounds <= 8 && bplf <= 8 && K <= 32 * W - 1 && free_e < 32) { JM = 1; RT = rounds; }
+  }
   int site_ok = 1;
   for (int k = 0; k < K; k++) { int ob; OWNER(m->site_body[k], ob); if (ob == 0) site_ok = 0; }
-  if (n_el > 31 || n_el < 1 || any_other || nquat != (free_j >= 0 ? 1 : 0) || (free_j >= 0 && free_e < 0) || JM == 0 || !site_ok) {
+  if (n_el < 1 || any_other || nquat != (free_j >= 0 ? 1 : 0) || (free_j >= 0 && free_e < 0) || JM == 0 || !site_ok) {
     free(loc); free(el); free(epar); free(edep);
     return NULL;
   }
@@ -159,8 +174,9 @@ static ofast *fast_create(const omodel *m, const osched *s) {
   F->free_adr = free_e >= 0 ? m->jnt_qposadr[free_j] : 0;
   F->free_e = free_e >= 0 ? free_e : 0;
   F->folded = fold;
+  F->W = W; F->NL = LANES * W; F->idl = F->NL - 1;
   char *covered = (char *)calloc(m->nq + 1, 1);
-  for (int l = 0; l < LANES; l++) {
+  for (int l = 0; l < F->NL; l++) {
     int on = l < n_el, b = on ? el[l] : 0;
     v3 bpos = { 0, 0, 0 }; q4 bquat = { 1, 0, 0, 0 };
     int nj = 0;
@@ -199,15 +215,15 @@ static ofast *fast_create(const omodel *m, const osched *s) {
     F->anc0[l] = add3(f_rotq(p0, bquat), bpos);
     F->ax0[l] = f_rotq(a0, bquat);
     for (int r = 0; r < RT; r++) {
-      int a = l >= n_el ? l : IDL;
+      int a = l >= n_el ? l : F->idl;
       if (on && r < rounds) { int t = eanc[(size_t)r * n_el + l]; if (t >= 0) a = t; }
       F->src[l][r] = a;
     }
-    F->par[l] = on ? (epar[l] >= 0 ? epar[l] : IDL) : l;
+    F->par[l] = on ? (epar[l] >= 0 ? epar[l] : F->idl) : l;
     int j0 = on && nj > 0 ? m->body_jntadr[b] : -1;
     int live = j0 >= 0 && s->jnt_e[j0] > s->jnt_s[j0];
     F->sa[l] = live ? s->jnt_s[j0] : 0; F->se[l] = live ? s->jnt_e[j0] : 0;
-    F->sk[l] = -1; F->seb[l] = IDL;
+    F->sk[l] = -1; F->seb[l] = F->idl;
     F->srel_p[l].x = F->srel_p[l].y = F->srel_p[l].z = R(0);
     F->srel_q[l].w = R(1); F->srel_q[l].x = F->srel_q[l].y = F->srel_q[l].z = R(0);
     if (l >= 1 && l <= K) {  /* site p on lane p + 1 */
@@ -226,18 +242,18 @@ static ofast *fast_create(const omodel *m, const osched *s) {
 }
 
 typedef struct {
-  v3 P[LANES]; q4 Q[LANES], Qp[LANES];
-  v3 lp[LANES][FJ]; q4 lq[LANES][FJ]; /* parent-frame pose of the body before hinge slot j >= 1 */
-  v3 s[LANES], res[LANES];
+  v3 P[FMAXL]; q4 Q[FMAXL], Qp[FMAXL];
+  v3 lp[FMAXL][FJ]; q4 lq[FMAXL][FJ]; /* parent-frame pose of the body before hinge slot j >= 1 */
+  v3 s[FMAXL], res[FMAXL];
   v3 fpos; q4 fq; REAL frinv;
 } ffwd;
 
 /* per-site data in lane order */
-typedef struct { v3 off[LANES], kp[LANES], km[LANES]; } fsites;
+typedef struct { v3 off[FMAXL], kp[FMAXL], km[FMAXL]; } fsites;
 
 static void fast_sites(const ofast *F, const REAL *site_pos, const REAL *kp, const REAL *kpmask, fsites *st) {
   memset(st, 0, sizeof(*st));
-  for (int l = 0; l < LANES; l++) {
+  for (int l = 0; l < F->NL; l++) {
     int k = F->sk[l];
     if (k < 0) continue;
     if (site_pos) st->off[l] = ld3(site_pos + 3 * k);
@@ -247,7 +263,7 @@ static void fast_sites(const ofast *F, const REAL *site_pos, const REAL *kp, con
   }
 }
 
-static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd *S) {
+static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[FMAXL][FNS], ffwd *S) {
   const int JM = F->JM, RT = F->RT;
   if (F->has_free) {
     S->fpos.x = pt[0][JM]; S->fpos.y = pt[1][JM]; S->fpos.z = pt[2][JM];
@@ -256,9 +272,9 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
   } else {
     S->fpos.x = S->fpos.y = S->fpos.z = R(0); S->fq.w = R(1); S->fq.x = S->fq.y = S->fq.z = R(0); S->frinv = R(1);
   }
-  q4 Q[LANES], Qn[LANES];
-  v3 lp[LANES];
-  for (int l = 0; l < LANES; l++) {
+  q4 Q[FMAXL], Qn[FMAXL];
+  v3 lp[FMAXL];
+  for (int l = 0; l < F->NL; l++) {
     REAL sh[FJ], ch[FJ];
     for (int j = 0; j < JM; j++) f_sincos((pt[l][j] - F->ref[l][j]) * R(0.5), &sh[j], &ch[j]);
     REAL ct = r_fma(ch[0], ch[0], -(sh[0] * sh[0])), sn = R(2) * (sh[0] * ch[0]);
@@ -280,21 +296,34 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
     }
     Q[l] = quat; lp[l] = pos;
   }
-  for (int r = 0; r < RT; r++) {
-    for (int l = 0; l < LANES; l++) Qn[l] = c_qmul(Q[F->src[l][r]], Q[l]);
-    memcpy(Q, Qn, sizeof(Q));
+  v3 v[FMAXL], vn[FMAXL];
+  if (F->W == 1) {  /* one warp: quaternions first, then ONE rotation per element and additive jumping of the positions */
+    for (int r = 0; r < RT; r++) {
+      for (int l = 0; l < F->NL; l++) Qn[l] = c_qmul(Q[F->src[l][r]], Q[l]);
+      memcpy(Q, Qn, sizeof(Q));
+    }
+    for (int l = 0; l < F->NL; l++) { S->Qp[l] = Q[F->par[l]]; v[l] = f_rotq(lp[l], S->Qp[l]); }
+    for (int r = 0; r < RT; r++) {
+      for (int l = 0; l < F->NL; l++) vn[l] = add3(v[F->src[l][r]], v[l]);
+      memcpy(v, vn, sizeof(v));
+    }
+  } else {          /* several warps: position and quaternion jump together, one exchange per round (stacb_wide.cuh) */
+    for (int l = 0; l < F->NL; l++) v[l] = lp[l];
+    for (int r = 0; r < RT; r++) {
+      for (int l = 0; l < F->NL; l++) {
+        int a = F->src[l][r];
+        vn[l] = add3(v[a], f_rotq(v[l], Q[a]));
+        Qn[l] = c_qmul(Q[a], Q[l]);
+      }
+      memcpy(Q, Qn, sizeof(Q)); memcpy(v, vn, sizeof(v));
+    }
+    for (int l = 0; l < F->NL; l++) S->Qp[l] = Q[F->par[l]];
   }
-  v3 v[LANES], vn[LANES];
-  for (int l = 0; l < LANES; l++) { S->Qp[l] = Q[F->par[l]]; v[l] = f_rotq(lp[l], S->Qp[l]); }
-  for (int r = 0; r < RT; r++) {
-    for (int l = 0; l < LANES; l++) vn[l] = add3(v[F->src[l][r]], v[l]);
-    memcpy(v, vn, sizeof(v));
-  }
-  REAL part[LANES];
-  for (int l = 0; l < LANES; l++) {
+  REAL part[FMAXL];
+  for (int l = 0; l < F->NL; l++) {
     S->P[l] = v[l]; S->Q[l] = Q[l];
   }
-  for (int l = 0; l < LANES; l++) {
+  for (int l = 0; l < F->NL; l++) {
     v3 pb = v[F->seb[l]]; q4 qb = Q[F->seb[l]];
     S->s[l] = add3(pb, f_rotq(st->off[l], qb));
     S->res[l].x = (st->kp[l].x - S->s[l].x) * st->km[l].x;
@@ -302,24 +331,32 @@ static REAL fast_fwd(const ofast *F, const fsites *st, REAL pt[LANES][FNS], ffwd
     S->res[l].z = (st->kp[l].z - S->s[l].z) * st->km[l].z;
     part[l] = r_fma(S->res[l].z, S->res[l].z, r_fma(S->res[l].y, S->res[l].y, S->res[l].x * S->res[l].x));
   }
-  return butterfly32(part);
+  return f_cta_sum(F->W, part);
 }
 
-static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANES][FNS]) {
+static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[FMAXL][FNS]) {
   const int JM = F->JM;
   v3 c = S->P[0];
-  REAL w[LANES][6], t2[LANES][6], wrl[LANES][6];
-  for (int l = 0; l < LANES; l++) {
+  REAL w[FMAXL][6], t2[FMAXL][6], wrl[FMAXL][6];
+  for (int l = 0; l < F->NL; l++) {
     v3 f = { R(-2) * S->res[l].x, R(-2) * S->res[l].y, R(-2) * S->res[l].z };
     v3 tq = c_cross(sub3(S->s[l], c), f);
     w[l][0] = f.x; w[l][1] = f.y; w[l][2] = f.z; w[l][3] = tq.x; w[l][4] = tq.y; w[l][5] = tq.z;
   }
-  for (int off = 1; off < LANES; off <<= 1) {
-    for (int l = 0; l < LANES; l++) for (int i = 0; i < 6; i++) t2[l][i] = (l >= off) ? w[l][i] + w[l - off][i] : w[l][i];
+  for (int off = 1; off < LANES; off <<= 1) {  /* Hillis-Steele inside every warp */
+    for (int l = 0; l < F->NL; l++) for (int i = 0; i < 6; i++) t2[l][i] = ((l % LANES) >= off) ? w[l][i] + w[l - off][i] : w[l][i];
     memcpy(w, t2, sizeof(w));
   }
+  if (F->W > 1) {  /* warp w >= 1 adds the totals of the warps before it, summed in warp order */
+    REAL offs[6], tot[8][6];
+    for (int ww = 0; ww < F->W; ww++) for (int i = 0; i < 6; i++) tot[ww][i] = w[LANES * ww + LANES - 1][i];
+    for (int ww = 1; ww < F->W; ww++) {
+      for (int i = 0; i < 6; i++) offs[i] = (ww == 1) ? tot[0][i] : offs[i] + tot[ww - 1][i];
+      for (int l = LANES * ww; l < LANES * (ww + 1); l++) for (int i = 0; i < 6; i++) w[l][i] = w[l][i] + offs[i];
+    }
+  }
   /* site p sits on lane p + 1: the inclusive scan at lane l is the sum over the sites p < l */
-  for (int l = 0; l < LANES; l++) {
+  for (int l = 0; l < F->NL; l++) {
     REAL *wr = wrl[l];
     for (int i = 0; i < 6; i++) wr[i] = w[F->se[l]][i] - w[F->sa[l]][i];
     v3 Fo = { wr[0], wr[1], wr[2] }, Tq = { wr[3], wr[4], wr[5] };
@@ -347,13 +384,13 @@ static void fast_bwd(const ofast *F, const ffwd *S, int free_wanted, REAL g[LANE
 }
 
 /* slot layout <-> qpos layout */
-static void fast_gather(const ofast *F, const REAL *q, REAL out[LANES][FNS]) {
-  for (int l = 0; l < LANES; l++) for (int m = 0; m <= F->JM; m++) out[l][m] = F->valid[l][m] ? q[F->adr[l][m]] : R(0);
+static void fast_gather(const ofast *F, const REAL *q, REAL out[FMAXL][FNS]) {
+  for (int l = 0; l < F->NL; l++) for (int m = 0; m <= F->JM; m++) out[l][m] = F->valid[l][m] ? q[F->adr[l][m]] : R(0);
 }
-static void fast_bits(const ofast *F, const uint8_t *qmask, int bits[LANES][FNS]) {
-  for (int l = 0; l < LANES; l++) for (int m = 0; m <= F->JM; m++) bits[l][m] = F->valid[l][m] && qmask[F->adr[l][m]];
+static void fast_bits(const ofast *F, const uint8_t *qmask, int bits[FMAXL][FNS]) {
+  for (int l = 0; l < F->NL; l++) for (int m = 0; m <= F->JM; m++) bits[l][m] = F->valid[l][m] && qmask[F->adr[l][m]];
 }
-static int fast_free_wanted(const ofast *F, int bits[LANES][FNS]) {
+static int fast_free_wanted(const ofast *F, int bits[FMAXL][FNS]) {
   if (!F->has_free) return 0;
   for (int l = 0; l < 7; l++) if (bits[l][F->JM]) return 1;
   return 0;
@@ -363,10 +400,10 @@ static REAL fast_lane_dot(int NS, const REAL *a, const REAL *b) {
   for (int m = 1; m < NS; m++) acc = r_fma(a[m], b[m], acc);
   return acc;
 }
-static REAL fast_dot(const ofast *F, REAL a[LANES][FNS], REAL b[LANES][FNS]) {
-  REAL part[LANES];
-  for (int l = 0; l < LANES; l++) part[l] = fast_lane_dot(F->JM + 1, a[l], b[l]);
-  return butterfly32(part);
+static REAL fast_dot(const ofast *F, REAL a[FMAXL][FNS], REAL b[FMAXL][FNS]) {
+  REAL part[FMAXL];
+  for (int l = 0; l < F->NL; l++) part[l] = fast_lane_dot(F->JM + 1, a[l], b[l]);
+  return f_cta_sum(F->W, part);
 }
 
 /* q_loss and its gradient in fast order; q, q0, grad in the qpos layout */
@@ -374,15 +411,15 @@ static REAL fast_loss_eval(const omodel *m, const ofast *F, const REAL *q, const
                            const REAL *kpmask, const REAL *site_pos, REAL *grad) {
   fsites st; ffwd S;
   fast_sites(F, site_pos, kp, kpmask, &st);
-  REAL qs[LANES][FNS], q0s[LANES][FNS], pt[LANES][FNS], g[LANES][FNS];
-  int bits[LANES][FNS];
+  REAL qs[FMAXL][FNS], q0s[FMAXL][FNS], pt[FMAXL][FNS], g[FMAXL][FNS];
+  int bits[FMAXL][FNS];
   fast_gather(F, q, qs); fast_gather(F, q0, q0s); fast_bits(F, qmask, bits);
-  for (int l = 0; l < LANES; l++) for (int mm = 0; mm <= F->JM; mm++) pt[l][mm] = bits[l][mm] ? qs[l][mm] : q0s[l][mm];
+  for (int l = 0; l < F->NL; l++) for (int mm = 0; mm <= F->JM; mm++) pt[l][mm] = bits[l][mm] ? qs[l][mm] : q0s[l][mm];
   REAL loss = fast_fwd(F, &st, pt, &S);
   if (grad) {
     fast_bwd(F, &S, fast_free_wanted(F, bits), g);
     for (int i = 0; i < m->nq; i++) grad[i] = R(0);
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm <= F->JM; mm++) if (bits[l][mm]) grad[F->adr[l][mm]] = g[l][mm];
+    for (int l = 0; l < F->NL; l++) for (int mm = 0; mm <= F->JM; mm++) if (bits[l][mm]) grad[F->adr[l][mm]] = g[l][mm];
   }
   return loss;
 }
@@ -393,14 +430,14 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
   const int NS = F->JM + 1;
   fsites st; ffwd S;
   fast_sites(F, site_pos, kp, kpmask, &st);
-  REAL q0s[LANES][FNS], x[LANES][FNS], y[LANES][FNS], g[LANES][FNS], xn[LANES][FNS], d[LANES][FNS], gt[LANES][FNS], pt[LANES][FNS];
-  REAL lbs[LANES][FNS], ubs[LANES][FNS], gm[LANES][FNS], dn[LANES][FNS];
-  int bits[LANES][FNS];
+  REAL q0s[FMAXL][FNS], x[FMAXL][FNS], y[FMAXL][FNS], g[FMAXL][FNS], xn[FMAXL][FNS], d[FMAXL][FNS], gt[FMAXL][FNS], pt[FMAXL][FNS];
+  REAL lbs[FMAXL][FNS], ubs[FMAXL][FNS], gm[FMAXL][FNS], dn[FMAXL][FNS];
+  int bits[FMAXL][FNS];
   fast_gather(F, q0, q0s); fast_gather(F, lb, lbs); fast_gather(F, ub, ubs); fast_bits(F, qmask, bits);
   const int fw = fast_free_wanted(F, bits);
   /* frozen slots (valid, not optimised): zero gradient; they stay at q0 inside the solve (unbounded effective box) and the squared
      length of the reference's one move to clip(q0) enters the first line search through sqn (solve_setup of stacb_fast.cuh) */
-  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
+  for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) {
     int frozen = F->valid[l][mm] && !bits[l][mm];
     gm[l][mm] = bits[l][mm] ? R(1) : R(0);
     dn[l][mm] = frozen ? clipr(q0s[l][mm], lbs[l][mm], ubs[l][mm]) - q0s[l][mm] : R(0);
@@ -410,10 +447,10 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
   /* passive coordinates: squared length of the move to clip(q0), dealt out over the lanes */
   REAL sqp;
   {
-    REAL part[LANES];
-    for (int l = 0; l < LANES; l++) {
+    REAL part[FMAXL];
+    for (int l = 0; l < F->NL; l++) {
       REAL acc = R(0); int first = 1;
-      for (int i = l; i < F->npassive; i += LANES) {
+      for (int i = l; i < F->npassive; i += F->NL) {
         int p = F->passive[i];
         REAL dd = clipr(q0[p], lb[p], ub[p]) - q0[p];
         acc = first ? dd * dd : r_fma(dd, dd, acc);
@@ -421,10 +458,10 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
       }
       part[l] = acc;
     }
-    sqp = sqn + butterfly32(part);
+    sqp = sqn + f_cta_sum(F->W, part);
   }
   memcpy(params, q0, sizeof(REAL) * m->nq);
-  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) { x[l][mm] = q0s[l][mm]; y[l][mm] = x[l][mm]; }
+  for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) { x[l][mm] = q0s[l][mm]; y[l][mm] = x[l][mm]; }
   REAL t = R(1), step = R(1), err = (REAL)INFINITY;
   solve_info info = { err, 0, 0 };
   if (maxiter <= 0) return info;
@@ -432,11 +469,11 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
     memcpy(pt, y, sizeof(pt));
     REAL fy = fast_fwd(F, &st, pt, &S);
     fast_bwd(F, &S, fw, g);
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) g[l][mm] = g[l][mm] * gm[l][mm];
+    for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) g[l][mm] = g[l][mm] * gm[l][mm];
     REAL stp = step;
     int halv = 0;
     for (;;) {
-      for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
+      for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) {
         xn[l][mm] = clipr(r_fma(-stp, g[l][mm], y[l][mm]), lbs[l][mm], ubs[l][mm]);
         d[l][mm] = xn[l][mm] - y[l][mm];
       }
@@ -454,11 +491,11 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
     ls_trace_push(halv);
     /* S holds the state of the accepted candidate: gradient at x+ */
     fast_bwd(F, &S, fw, gt);
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) gt[l][mm] = gt[l][mm] * gm[l][mm];
+    for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) gt[l][mm] = gt[l][mm] * gm[l][mm];
     step = (stp <= R(1e-6)) ? R(1) : stp / R(0.5);
     REAL tn = R(0.5) * (R(1) + r_sqrt(r_fma(R(4) * t, t, R(1))));
     REAL beta = (t - R(1)) / tn;
-    for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) {
+    for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) {
       y[l][mm] = r_fma(beta, xn[l][mm] - x[l][mm], xn[l][mm]);
       d[l][mm] = clipr(xn[l][mm] - gt[l][mm], lbs[l][mm], ubs[l][mm]) - xn[l][mm];
       x[l][mm] = xn[l][mm];
@@ -469,7 +506,7 @@ static solve_info fast_q_opt(const omodel *m, const ofast *F, const REAL *q0, co
   } while (err > tol && info.iters < maxiter);
   info.error = err;
   for (int i = 0; i < F->npassive; i++) { int p = F->passive[i]; params[p] = clipr(q0[p], lb[p], ub[p]); }
-  for (int l = 0; l < LANES; l++) for (int mm = 0; mm < NS; mm++) if (F->valid[l][mm]) {
+  for (int l = 0; l < F->NL; l++) for (int mm = 0; mm < NS; mm++) if (F->valid[l][mm]) {
     int a = F->adr[l][mm];
     params[a] = bits[l][mm] ? x[l][mm] : clipr(x[l][mm], lb[a], ub[a]);  /* the reference's iterate of a frozen coordinate is clip(q0) */
   }

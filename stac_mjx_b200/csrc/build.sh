@@ -20,6 +20,10 @@ for v in $FAST; do
   $NVCC $FLAGS -Xptxas -v -DV_FJM=$1 -DV_FRT=$2 -DV_FNBF=$3 -c stacb_fast_variant.cu -o _obj/fast_$v.o > _obj/fast_$v.log 2>&1 &
   pids="$pids $!"
 done
+for w in 2 4 6 8; do
+  $NVCC $FLAGS -Xptxas -v -DV_WW=$w -c stacb_wide_variant.cu -o _obj/wide_$w.o > _obj/wide_$w.log 2>&1 &
+  pids="$pids $!"
+done
 $NVCC $FLAGS -c stacb_abi.cu -o _obj/abi.o > _obj/abi.log 2>&1 &
 pids="$pids $!"
 $NVCC $FLAGS -c stacb_post.cu -o _obj/post.o > _obj/post.log 2>&1 &

@@ -66,6 +66,7 @@ struct stacb_tree {
   int cpl, bpl_act, bpl_full, jm_act;
   bool fast_ok = false;                  // the register-resident hinge-tree solver applies (stacb_fast.cuh)
   int fast_rounds = 0;                   // pointer-jumping rounds of its element set
+  int wide_W = 0;                        // > 0: the element set needs this many warps per evaluation (stacb_wide.cuh)
   std::atomic<int> mode{-1};             // scheduling override of stacb_pose_clips (stacb_tree_set_mode)
   std::atomic<int> path{0};              // 0 = register-resident solver where it applies, 1 = general kernels only
   std::vector<void *> allocs;
@@ -353,7 +354,7 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
       std::vector<int> rec_e, anc_e, site_el;
       std::vector<float> site_rel;
       int re = 0, n_el = 0;
-      if (build_folded_set(m, act, subsize, order, rec_e, anc_e, re, site_el, site_rel, n_el) && n_el <= 31 && n_el >= 1 && re <= RMAX) {
+      if (build_folded_set(m, act, subsize, order, rec_e, anc_e, re, site_el, site_rel, n_el) && n_el <= 255 && n_el >= 1 && re <= RMAX) {
         T.fs.n = n_el; T.fs.rounds = re;
         const float *rel_dev = nullptr;
         if ((rc = upload(t, rec_e, &T.fs.rec)) || (rc = upload(t, anc_e, &T.fs.anc)) || (rc = upload(t, site_el, &T.site_efs)) ||
@@ -366,10 +367,13 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
         for (int e = 0; e < n_el; e++)
           if (rec_e[(size_t)e * REC + R_BODY] == (T.free_e >= 0 ? rec_a[(size_t)T.free_e * REC + R_BODY] : -1)) T.fs_free_e = e;
         t->fast_rounds = re;
-        fits_warp = T.free_e < 0 || T.fs_free_e >= 0;
+        fits_warp = (T.free_e < 0 || T.fs_free_e >= 0) && n_el <= 31;
+        if (n_el > 31 && (T.free_e < 0 || (T.fs_free_e >= 0 && T.fs_free_e < 32))) t->wide_W = 2 * ((n_el + 1 + 63) / 64);  // 2, 4, 6 or 8 warps
       }
     }
-    t->fast_ok = fits_warp && K <= 31 && !T.any_other && T.nquat == (T.free_e >= 0 ? 1 : 0) && (passive.empty() || passive[0] >= 3);
+    const bool common = !T.any_other && T.nquat == (T.free_e >= 0 ? 1 : 0) && (passive.empty() || passive[0] >= 3);
+    t->fast_ok = fits_warp && K <= 31 && common;
+    if (!(t->wide_W >= 2 && t->wide_W <= 8 && common && K <= 32 * t->wide_W - 1)) t->wide_W = 0;
   }
   void *cnt = nullptr;
   if (cudaMalloc(&cnt, kCounterPool * sizeof(int)) != cudaSuccess) { stacb_tree_destroy(t); return fail(STACB_E_CUDA, "cudaMalloc(counter)"); }
@@ -399,10 +403,20 @@ STACB_VARIANTS(X)
   cudaError_t launch_fast_batch_##j##_##r##_##f(const DevTree &, const BatchArgs &, int, int, cudaStream_t);
 STACB_FAST_VARIANTS(X)
 #undef X
+#define STACB_WIDE_WARPS(X) X(2) X(4) X(6) X(8)
+#define X(w)                                                                                            \
+  cudaError_t launch_wide_pose_##w(const DevTree &, const PoseArgs &, int, size_t, cudaStream_t);        \
+  cudaError_t launch_wide_batch_##w(const DevTree &, const BatchArgs &, int, cudaStream_t);
+STACB_WIDE_WARPS(X)
+#undef X
 }  // namespace stacb
 
 static bool fits_fast(const stacb_tree *t, int jm, int rt, int nbf) {
   return t->fast_ok && t->path.load() == 0 && t->jm_act <= jm && t->fast_rounds <= rt && t->bpl_full <= nbf;
+}
+
+static bool fits_wide(const stacb_tree *t) {
+  return t->wide_W >= 2 && t->path.load() == 0 && t->jm_act <= 1 && t->fast_rounds <= 8 && t->bpl_full <= 8;
 }
 
 static bool fits(const stacb_tree *t, int cpl, int nb, int nbf, int spl, int jm) {
@@ -418,6 +432,14 @@ static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
   const int g_force_mode = t->mode.load();
+  if (fits_wide(t)) {  // wide hinge trees: W warps per chain, one chain per CTA (the scheduling mode does not apply)
+    const size_t area = ((size_t)2 * t->T.nqp + 7 * (size_t)t->T.pqn) * 4;
+    const int grid = std::min(a.C, sms * 8);
+#define X(w) \
+  if (t->wide_W == w) { CUDA_TRY(launch_wide_pose_##w(t->T, a, grid, area, s)); return STACB_OK; }
+    STACB_WIDE_WARPS(X)
+#undef X
+  }
   {
     // register-resident solver: latency mode (2 * NC warps per chain) for few chains, throughput mode (one warp per chain)
     // for many, dense throughput mode (registers capped for 16 warps per SM) from 16 chains per SM
@@ -468,6 +490,13 @@ static int run_batch(const stacb_tree *t, const BatchArgs &a, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
   const int wpb = (a.B <= 2 * sms) ? 1 : 4;
   const int grid = std::min((a.B + wpb - 1) / wpb, sms * 16);
+  if ((a.mode == 1 || a.mode == 2) && fits_wide(t)) {
+    const int wgrid = std::min(a.B, sms * 8);
+#define X(w) \
+  if (t->wide_W == w) { CUDA_TRY(launch_wide_batch_##w(t->T, a, wgrid, s)); return STACB_OK; }
+    STACB_WIDE_WARPS(X)
+#undef X
+  }
   if (a.mode == 1 || a.mode == 2) {  // q_loss / _q_opt share the arithmetic of the pose kernel that serves this model
 #define X(j, r, f) \
   if (fits_fast(t, j, r, f)) { CUDA_TRY(launch_fast_batch_##j##_##r##_##f(t->T, a, grid, 32 * wpb, s)); return STACB_OK; }
@@ -598,6 +627,7 @@ extern "C" int stacb_tree_set_path(stacb_tree *t, int path) {
 
 extern "C" int stacb_tree_path(const stacb_tree *t) {
   if (!t) return -1;
+  if (fits_wide(t)) return 1;
 #define X(j, r, f) \
   if (fits_fast(t, j, r, f)) return 1;
   STACB_FAST_VARIANTS(X)

@@ -77,7 +77,7 @@ struct Fwd {
 };
 
 template <int JM, int RT>
-__device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, int lane) {
+__device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, int lane, int idl = IDL) {
   const DevSet &S = T.fs;
   const bool on = lane < S.n;
   BodyConst b;
@@ -111,18 +111,18 @@ __device__ __forceinline__ void lane_init(LaneC<JM, RT> &L, const DevTree &T, in
   L.ax[0] = rotq(a0, b.quat);
 #pragma unroll
   for (int r = 0; r < RT; r++) {
-    int a = lane >= S.n ? lane : IDL;
+    int a = lane >= S.n ? lane : idl;
     if (on && r < S.rounds) { const int t = __ldg(S.anc + r * S.n + lane); if (t >= 0) a = t; }
     L.src[r] = a;
   }
-  L.par = on ? (b.parent >= 0 ? b.parent : IDL) : lane;
+  L.par = on ? (b.parent >= 0 ? b.parent : idl) : lane;
   const bool live = on && b.nj > 0 && b.jse[0] > b.jsa[0];
   L.sa = live ? b.jsa[0] : 0;
   L.se = live ? b.jse[0] : 0;
 }
 
-__device__ __forceinline__ void site_init(SiteC &st, const DevTree &T, int lane, const float *__restrict__ site_pos) {
-  st.k = -1; st.eb = IDL; st.ef = 0;
+__device__ __forceinline__ void site_init(SiteC &st, const DevTree &T, int lane, const float *__restrict__ site_pos, int idl = IDL) {
+  st.k = -1; st.eb = idl; st.ef = 0;
   st.off = mk3(0.f, 0.f, 0.f); st.kp = mk3(0.f, 0.f, 0.f); st.km = mk3(0.f, 0.f, 0.f);
   if (lane >= 1 && lane <= T.K) {
     st.k = __ldg(T.site_order + lane - 1);

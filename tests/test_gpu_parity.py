@@ -98,7 +98,7 @@ def test_clips_match_golden(name, engine_of):
         assert np.array_equal(o[k], E(g, f"clip_{k}")), f"{k} no longer bit-identical to the canonical oracle"
 
 
-@pytest.mark.parametrize("name", ["rodent", "celegans", "synth_data", "fly_treadmill"])
+@pytest.mark.parametrize("name", ["rodent", "celegans", "synth_data", "fly_treadmill", "mouse"])
 def test_general_kernels_still_serve_the_fast_models(name, engine_of):
     """Engine.set_path(1): the general kernels (canonical order, oracle mode 1) on the models the register-resident solver
     serves by default -- loss / gradient, single solves and clips against the committed c32 vectors, bit for bit."""
