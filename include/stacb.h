@@ -177,7 +177,8 @@ int stacb_tree_set_mode(stacb_tree *tree, int mode);
 /* Which kernels serve the handle: 0 (default) = the register-resident hinge-tree solver where the model qualifies (active
  * subtree of at most 31 bodies with hinge joints plus one free joint, at most 31 keypoint sites: rodent, C. elegans), the
  * general kernels elsewhere; 1 = general kernels only.  (Jointless -- welded -- active bodies are folded into their nearest
- * jointed ancestor first, which brings the fruitfly's 49-57 active bodies down to 25 elements.)  The two paths evaluate the same mathematics in different (each
+ * jointed ancestor first, which brings the fruitfly's 49-57 active bodies down to 25 elements; hinge trees of 32-255 elements with
+ * one hinge per element -- the mouse -- run the same solver on 2-8 warps per chain.)  The two paths evaluate the same mathematics in different (each
  * fixed and documented) float32 operation orders, so their results agree to rounding, not bit for bit.
  * stacb_tree_path returns 1 when the register-resident solver serves the handle, 0 otherwise. */
 int stacb_tree_set_path(stacb_tree *tree, int path);

@@ -405,7 +405,7 @@ STACB_FAST_VARIANTS(X)
 #undef X
 #define STACB_WIDE_WARPS(X) X(2) X(4) X(6) X(8)
 #define X(w)                                                                                            \
-  cudaError_t launch_wide_pose_##w(const DevTree &, const PoseArgs &, int, size_t, cudaStream_t);        \
+  cudaError_t launch_wide_pose_##w(const DevTree &, const PoseArgs &, int, size_t, int, cudaStream_t);   \
   cudaError_t launch_wide_batch_##w(const DevTree &, const BatchArgs &, int, cudaStream_t);
 STACB_WIDE_WARPS(X)
 #undef X
@@ -436,7 +436,7 @@ static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
     const size_t area = ((size_t)2 * t->T.nqp + 7 * (size_t)t->T.pqn) * 4;
     const int grid = std::min(a.C, sms * 8);
 #define X(w) \
-  if (t->wide_W == w) { CUDA_TRY(launch_wide_pose_##w(t->T, a, grid, area, s)); return STACB_OK; }
+  if (t->wide_W == w) { CUDA_TRY(launch_wide_pose_##w(t->T, a, grid, area, (g_force_mode < 0 ? a.C > sms : g_force_mode == 2) ? 1 : 0, s)); return STACB_OK; }
     STACB_WIDE_WARPS(X)
 #undef X
   }

@@ -302,8 +302,9 @@ __device__ __forceinline__ float passive_sq_w(const DevTree &T, const UniW &u, c
 }
 
 // One chain per CTA of W warps; frames sequential; the stage loop of fast::fast_pose_kernel.
-template <int W, int NBF>
-__global__ void __launch_bounds__(32 * W, 1) wide_pose_kernel(DevTree T, PoseArgs a) {
+// MINB: CTAs per SM the registers are capped for (2 once there are more chains than SMs and two CTAs fit the register file)
+template <int W, int NBF, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, PoseArgs a) {
   extern __shared__ float smem[];
   __shared__ int s_chain;
   __shared__ float s_beta[BT + 1];

@@ -6,8 +6,8 @@ namespace stacb {
 #define FN_(prefix, a) prefix##a
 #define FN(prefix, a) FN_(prefix, a)
 
-cudaError_t FN(launch_wide_pose_, V_WW)(const DevTree &T, const PoseArgs &a, int grid, size_t area_bytes, cudaStream_t s) {
-  auto k = wide::wide_pose_kernel<V_WW, 8>;
+cudaError_t FN(launch_wide_pose_, V_WW)(const DevTree &T, const PoseArgs &a, int grid, size_t area_bytes, int dense, cudaStream_t s) {
+  auto k = (dense && V_WW <= 6) ? wide::wide_pose_kernel<V_WW, 8, (V_WW <= 6 ? 2 : 1)> : wide::wide_pose_kernel<V_WW, 8, 1>;
   const size_t smem = area_bytes + sizeof(wide::WX<V_WW>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
