@@ -577,3 +577,47 @@ def test_random_trees_with_welded_bodies_on_the_register_resident_path(seed):
     L0, G0 = [npy(x) for x in Engine(t, sb, 0).loss_grad(q, q0, kp, qm, km, off)]
     np.testing.assert_allclose(L1, L0, rtol=2e-5)
     np.testing.assert_allclose(G1, G0, atol=2e-5 * max(1.0, np.abs(G0).max()))
+
+
+@pytest.mark.parametrize("seed,n_bodies,n_sites,p_welded", [(21, 70, 20, 0.1), (22, 140, 40, 0.1), (23, 250, 60, 0.1), (25, 250, 140, 0.02), (26, 254, 160, 0.0)])
+def test_random_wide_trees_on_the_multi_warp_path(seed, n_bodies, n_sites, p_welded):
+    """Random single-hinge trees of 34 .. 200+ jointed elements: the multi-warp register-resident kernels (2, 4, 6, 8 warps per
+    chain) against oracle mode 2, bit for bit -- loss / gradient, masked solves, a clip with root optimisation, both register caps."""
+    from oracle.oracle import Oracle
+    from random_trees import random_tree
+    from stac_mjx_b200.engine import Engine
+
+    t, site_idxs, lb, ub = random_tree(seed, n_bodies=n_bodies, p_welded=p_welded, max_hinges=1, n_sites=n_sites)
+    sb, off = t.site_bodyid[site_idxs], t.site_pos[site_idxs].astype(np.float32)
+    K = len(sb)
+    eng, o = Engine(t, sb, 0), Oracle(t, sb, np.float32, 2)
+    assert eng.path == 1 and o.fast_path
+    rng = np.random.default_rng(seed)
+    q = (t.qpos0 + rng.normal(scale=0.2, size=(4, t.nq))).astype(np.float32)
+    q0 = (q + rng.normal(scale=0.05, size=q.shape)).astype(np.float32)
+    kp = np.stack([o.fk(q[(i + 1) % 4], off)[3].reshape(-1) for i in range(4)]).astype(np.float32) + 0.004
+    qm, km = np.ones(t.nq, bool), np.ones(3 * K, bool)
+    part = rng.random(t.nq) < 0.5
+    for mask in (qm, part):
+        L, G = [npy(x) for x in eng.loss_grad(q, q0, kp, mask, km, off)]
+        for i in range(4):
+            l, g = o.loss_grad(q[i], q0[i], mask, kp[i], km, off)
+            assert float(l) == float(L[i])
+            np.testing.assert_array_equal(G[i], g)
+    qs = q[:2].copy()
+    qs[:, 8:12] += 9.0
+    p, e, it, ls = [npy(x) for x in eng.q_opt(qs, kp[:2], part, km, off, lb, ub, 1e-5, maxiter=25)]
+    for i in range(2):
+        po, eo, ito, lso = o.q_opt(qs[i], lb, ub, part, kp[i], km, off, 1e-5, maxiter=25)
+        assert (it[i], ls[i]) == (ito, lso)
+        np.testing.assert_array_equal(p[i], po)
+    kpc = kp.reshape(2, 2, -1)
+    kw = dict(do_root=1, root_kp_idx=0, trunk_kps=np.ones(K, bool), tol=1e-5, maxiter=30)
+    ref = o.pose_clips(kpc, t.qpos0, off, lb, ub, part[None], **kw)
+    for mode in (0, 2):
+        eng.set_mode(mode)
+        qio = torch.tensor(np.tile(t.qpos0.astype(np.float32), (2, 1)), device=eng.device)
+        out = eng.pose_clips(kpc, qio, off, lb, ub, part[None], **kw)
+        np.testing.assert_array_equal(npy(out["iters"]), ref["iters"])
+        for k in ("qpos", "xpos", "xquat", "sites", "err"):
+            np.testing.assert_array_equal(npy(out[k]), ref[k], err_msg=f"mode {mode} {k}")

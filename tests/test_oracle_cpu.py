@@ -383,3 +383,32 @@ def test_fast_order_on_random_trees_with_welded_bodies(seed):
     r0 = o0.q_opt(q, lb, ub, qm, kp, km, off, 1e-9, maxiter=15)
     r2 = o2.q_opt(q, lb, ub, qm, kp, km, off, 1e-9, maxiter=15)
     np.testing.assert_allclose(r2[0], r0[0], atol=2e-4)
+
+
+@pytest.mark.parametrize("seed,n_bodies,n_sites,p_welded", [(21, 70, 20, 0.1), (22, 140, 40, 0.1), (23, 250, 60, 0.1), (25, 250, 140, 0.02), (26, 254, 160, 0.0)])
+def test_wide_order_on_random_trees(seed, n_bodies, n_sites, p_welded):
+    """Random single-hinge trees of 34 .. 200+ jointed elements (2, 4, 6, 8 warps per evaluation, more sites than one warp holds,
+    welded bodies folded): oracle mode 2 in its multi-warp order against the MJX order and reverse-mode autodiff."""
+    from random_trees import n_active, random_tree
+
+    t, site_idxs, lb, ub = random_tree(seed, n_bodies=n_bodies, p_welded=p_welded, max_hinges=1, n_sites=n_sites)
+    sb, off = t.site_bodyid[site_idxs], t.site_pos[site_idxs]
+    na, nj = n_active(t, sb)
+    o0, o2 = Oracle(t, sb, np.float64, 0), Oracle(t, sb, np.float64, 2)
+    assert o2.fast_path and nj > 31
+    rng = np.random.default_rng(seed)
+    T = TorchModel(t, sb)
+    qm, km = np.ones(t.nq, bool), np.ones(3 * len(sb), bool)
+    part = rng.random(t.nq) < 0.5
+    q = t.qpos0 + rng.normal(scale=0.2, size=t.nq)
+    q0 = q + rng.normal(scale=0.05, size=t.nq)
+    kp = o0.fk(t.qpos0 + rng.normal(scale=0.2, size=t.nq), off)[3].reshape(-1) + 0.003
+    for mask in (qm, part):
+        a, b = o0.loss_grad(q, q0, mask, kp, km, off), o2.loss_grad(q, q0, mask, kp, km, off)
+        L, G = T.loss_grad(q, q0, mask, kp, km, off)
+        assert abs(float(a[0]) - float(b[0])) < 2e-6 * max(1e-3, float(a[0]))
+        np.testing.assert_allclose(b[1], a[1], atol=2e-6 * max(1.0, np.abs(a[1]).max()))
+        np.testing.assert_allclose(b[1], G, atol=2e-6 * max(1.0, np.abs(G).max()))
+    r0 = o0.q_opt(q, lb, ub, qm, kp, km, off, 1e-9, maxiter=10)
+    r2 = o2.q_opt(q, lb, ub, qm, kp, km, off, 1e-9, maxiter=10)
+    np.testing.assert_allclose(r2[0], r0[0], atol=2e-4)
