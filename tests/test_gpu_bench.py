@@ -37,5 +37,6 @@ def test_bench_line_contract():
     m = p["vs_mjx_order_f32"]  # another float32 order of the same algorithm: the typical frame meets north_star's tolerances
     assert m["marker_abs_m"]["median"] <= 1e-4 and m["qpos_abs_rad"]["median"] <= 1e-3 and m["marker_rmse_m"] <= 1e-3
     assert d["config5_1e6_frames"]["value"] > 0 and d["config5_1e6_frames"]["scaling"] == "strong"
+    assert d["config4_fruitfly"]["value"] > 0 and d["config5_mouse"]["value"] > 0 and "register-resident" in d["config5_mouse"]["workload"]
     assert d["config2_weak"]["value"] > 0 and d["config3_fit"]["seconds"] > 0 and d["config3_fit"]["offsets_finite"] is True
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
