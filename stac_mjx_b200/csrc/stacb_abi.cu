@@ -245,6 +245,25 @@ extern "C" int stacb_tree_create(const stacb_tree_desc *d, int device, stacb_tre
   if (!d || !out) return fail(STACB_E_INVALID, "null argument");
   const stacb_tree_desc &m = *d;
   if (m.nbody < 2 || m.nq < 1 || m.njnt < 0 || m.nsite < 1) return fail(STACB_E_INVALID, "empty model");
+  if (!m.body_parent || !m.body_jntadr || !m.body_jntnum || !m.body_pos || !m.body_quat || !m.qpos0 || !m.site_body ||
+      (m.njnt > 0 && (!m.jnt_type || !m.jnt_qposadr || !m.jnt_pos || !m.jnt_axis)))
+    return fail(STACB_E_INVALID, "null array in the model description");
+  {  // every joint belongs to exactly one body's [jntadr, jntadr + jntnum) range and its coordinates lie inside qpos
+    static const int width[4] = {7, 4, 1, 1};
+    int owned = 0;
+    for (int b = 0; b < m.nbody; b++) {
+      const int n = m.body_jntnum[b];
+      if (n < 0 || (n > 0 && (m.body_jntadr[b] < 0 || m.body_jntadr[b] + n > m.njnt)))
+        return fail(STACB_E_INVALID, "body_jntadr / body_jntnum outside the joint arrays");
+      owned += n;
+    }
+    if (owned != m.njnt || m.body_jntnum[0] != 0) return fail(STACB_E_INVALID, "joints must be owned by non-world bodies, each by exactly one");
+    for (int j = 0; j < m.njnt; j++) {
+      const int t = m.jnt_type[j];
+      if (t < 0 || t > 3) return fail(STACB_E_INVALID, "unknown joint type");
+      if (m.jnt_qposadr[j] < 0 || m.jnt_qposadr[j] + width[t] > m.nq) return fail(STACB_E_INVALID, "jnt_qposadr outside qpos");
+    }
+  }
   std::vector<int> path_stack{0};  // depth-first pre-order <=> every body's parent is on the current root-to-node path
   for (int b = 1; b < m.nbody; b++) {
     if (m.body_parent[b] < 0 || m.body_parent[b] >= b) return fail(STACB_E_INVALID, "body ids must be in depth-first pre-order");

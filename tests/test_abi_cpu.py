@@ -106,6 +106,45 @@ def test_tree_create_rejects_body_orders_that_are_not_depth_first():
     assert b"depth-first pre-order" in L.stacb_last_error()
 
 
+def test_tree_create_rejects_malformed_descriptions():
+    """Joint ranges, joint types and qpos addresses are validated before anything is dereferenced on their strength (no GPU)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from stac_mjx_b200 import _lib
+
+    L = _lib.lib()
+
+    def create(nq=2, jadr=(-1, 0, 1), jnum=(0, 1, 1), jtype=(3, 3), jq=(0, 1), null_field=None):
+        nb = 3
+        parent = np.array([0, 0, 1], np.int32)
+        pos, quat = np.zeros((nb, 3), np.float32), np.tile(np.array([1, 0, 0, 0], np.float32), (nb, 1))
+        jp, ja = np.zeros((2, 3), np.float32), np.tile(np.array([0, 0, 1], np.float32), (2, 1))
+        keep = [parent, np.array(jadr, np.int32), np.array(jnum, np.int32), pos, quat, np.array(jtype, np.int32), np.array(jq, np.int32),
+                np.array([1, 2], np.int32), jp, ja, np.zeros(max(nq, 1), np.float32), np.array([2], np.int32)]  # fmt: skip
+        ptrs = [a.ctypes.data_as(C.c_void_p) for a in keep]
+        if null_field is not None:
+            ptrs[null_field] = C.c_void_p()
+        d = _lib.TreeDesc(nb, nq, 2, 1, *ptrs)
+        h = C.c_void_p()
+        rc = L.stacb_tree_create(C.byref(d), 0, C.byref(h))
+        return rc, L.stacb_last_error()
+
+    rc, msg = create(null_field=3)
+    assert rc == -1 and b"null array" in msg
+    rc, msg = create(jadr=(-1, 0, 2))  # joint range past the joint arrays
+    assert rc == -1 and b"body_jntadr" in msg
+    rc, msg = create(jnum=(0, 1, 0))  # a joint nobody owns
+    assert rc == -1 and b"exactly one" in msg
+    rc, msg = create(jtype=(3, 7))
+    assert rc == -1 and b"unknown joint type" in msg
+    rc, msg = create(jq=(0, 2))  # coordinate address outside qpos
+    assert rc == -1 and b"jnt_qposadr" in msg
+    rc, msg = create(jtype=(3, 1), jq=(0, 1))  # a ball joint needs four coordinates
+    assert rc == -1 and b"jnt_qposadr" in msg
+
+
 def test_xla_ffi_handlers_type_check_against_a_mock_of_the_ffi_api():
     """csrc/stacb_xla_ffi.cc cannot be built here (no jaxlib headers).  It is compiled (-fsyntax-only) against a mock with the shape
     of xla/ffi/api/ffi.h: every handler must be invocable with exactly the argument list its binding declares, and every C ABI
