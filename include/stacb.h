@@ -154,7 +154,9 @@ int stacb_m_scratch_floats(const stacb_tree *tree, int T);
  *   c+1 ((1-w) a + w b in float64, rounded to float32 as numpy does), then first clip whole, middle clips [ov:], last clip [ov:-ov].
  *   w [ov] float64 (device): the reference's sigmoid 0.5 (1 + tanh(10 (x - 0.5) / 2)), x = linspace(0, 1, ov).
  * stacb_qvel -- utils.compute_velocity_from_kinematics (stac_mjx/utils.py:302-347) for C continuous clips:
- *   qpos [C,F,nq] -> qvel [C,F,nv], nv = nq-1 with a free joint (first 7 qpos), else nq; the last frame of a clip gets zero velocity. */
+ *   qpos [C,F,nq] -> qvel [C,F,nv], nv = nq-1 with a free joint (first 7 qpos), else nq; the last frame of a clip gets zero velocity.
+ * Neither takes a handle: they launch on the calling thread's current CUDA device, which must be the device `stream` belongs to.
+ * w may be null when ov == 0 (nothing is blended). */
 long long stacb_edge_rows(int C, int F, int ov);
 int stacb_edge_crossfade(const float *in, const double *w, float *out, int C, int F, int ov, int D, void *stream);
 int stacb_qvel(const float *qpos, float *qvel, int C, int F, int nq, int freejoint, float dt, float max_qvel, void *stream);

@@ -90,7 +90,7 @@ extern "C" long long stacb_edge_rows(int C, int F, int ov) {
 }
 
 extern "C" int stacb_edge_crossfade(const float *in, const double *w, float *out, int C, int F, int ov, int D, void *stream) {
-  if (!in || !w || !out || C < 1 || D < 1 || ov < 0 || F < ov) return post_fail(STACB_E_INVALID, "stacb_edge_crossfade: bad argument");
+  if (!in || (!w && ov > 0) || !out || C < 1 || D < 1 || ov < 0 || F < ov) return post_fail(STACB_E_INVALID, "stacb_edge_crossfade: bad argument");
   const long long rows = stacb_edge_rows(C, F, ov), total = rows * D;
   const int block = 256;
   const int grid = (int)std::min<long long>((total + block - 1) / block, 148LL * 32);

@@ -28,6 +28,10 @@ class Engine:
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.StacbError(f"the STAC solver path runs on CUDA devices only, not {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.tree = tree
         self.nq, self.nbody, self.K = tree.nq, tree.nbody, len(site_bodies)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -39,7 +43,7 @@ class Engine:
         ]  # fmt: skip
         desc = _lib.TreeDesc(tree.nbody, tree.nq, tree.njnt, self.K, *[a.ctypes.data_as(C.c_void_p) for a in keep])
         h = C.c_void_p()
-        _lib.check(L.stacb_tree_create(C.byref(desc), self.device.index or 0, C.byref(h)), "stacb_tree_create")
+        _lib.check(L.stacb_tree_create(C.byref(desc), self.device.index, C.byref(h)), "stacb_tree_create")
         self._h, self._L = h, L
 
     def __del__(self):
@@ -157,12 +161,20 @@ class Engine:
         trunk = self.u8(trunk_kps if trunk_kps is not None else np.ones(self.K), (self.K,))
         if out is None:
             out = {}
-        o = lambda k, *shape, dtype=torch.float32: out.setdefault(k, self.empty(*shape, dtype=dtype))
+
+        def o(k, *shape, dtype=torch.float32, zero=False):
+            t = out.get(k)
+            if t is None:  # first use of this dict: allocate (later calls with the same C, F reuse the buffers)
+                t = out[k] = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+            elif not (isinstance(t, torch.Tensor) and tuple(t.shape) == shape and t.dtype == dtype and t.device == self.device and t.is_contiguous()):
+                raise ValueError(f"out[{k!r}] must be a contiguous {dtype} tensor of shape {shape} on {self.device} (the kernel writes it in place)")
+            return t
+
         qpos, xpos = o("qpos", Cn, F, self.nq), o("xpos", Cn, F, self.nbody, 3)
         xquat, sites, err = o("xquat", Cn, F, self.nbody, 4), o("sites", Cn, F, self.K, 3), o("err", Cn, F)
         if want_stats:
             iters, ls = o("iters", Cn, F, 1 + P, dtype=torch.int32), o("ls_evals", Cn, F, 1 + P, dtype=torch.int32)
-            rs = out.setdefault("root_stats", torch.zeros(Cn, 4, dtype=torch.int32, device=self.device))
+            rs = o("root_stats", Cn, 4, dtype=torch.int32, zero=True)
         else:
             iters = ls = rs = None
         status = o("status", Cn, dtype=torch.int32)

@@ -244,6 +244,14 @@ def test_edge_cases(rodent, engine_of):
     assert empty["qpos"].shape[0] == 0
     with pytest.raises(ValueError):
         eng.pose_clips(np.zeros((1, 3, 5), np.float32), qio[:1], s.initial_offsets, s.lb, s.ub, s.indiv_parts, do_root=0)
+    # a reused output dict is written in place: buffers of another launch shape are refused, matching ones are reused
+    with pytest.raises(ValueError, match="out\\['qpos'\\]"):
+        eng.pose_clips(kp.reshape(4, 1, -1)[:2], qio[:2].clone(), s.initial_offsets, s.lb, s.ub, np.zeros((0, rodent.tree.nq), bool), out=out, **rodent.root_kw())
+    ptr = out["qpos"].data_ptr()
+    again = eng.pose_clips(kp.reshape(4, 1, -1), torch.tensor(np.tile(rodent.tree.qpos0.astype(np.float32), (4, 1)), device=eng.device),
+                           s.initial_offsets, s.lb, s.ub, np.zeros((0, rodent.tree.nq), bool), out=out, **rodent.root_kw())  # fmt: skip
+    assert again["qpos"].data_ptr() == ptr
+    np.testing.assert_allclose(npy(again["qpos"]), ref["qpos"], atol=QPOS_TOL, rtol=0)
     # maxiter = 1: exactly one FISTA iteration per solve
     one = eng.pose_clips(kp.reshape(4, 1, -1), qio.clone(), s.initial_offsets, s.lb, s.ub, s.indiv_parts, do_root=0, maxiter=1)
     assert (npy(one["iters"]) == 1).all()
