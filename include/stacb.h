@@ -171,7 +171,9 @@ int stacb_fma_peak(float *out, int blocks, int threads, int iters, void *stream)
  * chain speculating on three line-search candidates; general path: each of the four speculative evaluations carried out by
  * three warps sharing the bodies of a wide tree), 4 pair mode (register-resident path: two warps per chain evaluate two line-search
  * candidates at once, then the accepted point's gradient and the next extrapolation at once; chosen automatically between one
- * chain per SM and four).  Results do not depend on the mode (bit-identical).
+ * chain per SM and four).  On the multi-warp register-resident path (W = 2..8 warps per evaluation) 0 and 3 mean one group of W
+ * warps per chain, 2 the same with registers capped for two CTAs per SM, 1 and 4 two groups of W warps per chain (pair mode; chosen
+ * automatically only for W = 2 with at most one chain per SM).  Results do not depend on the mode (bit-identical).
  * The setting is a property of the handle, not of the process; do not change it while a launch of the same handle is being
  * enqueued from another thread. */
 int stacb_tree_set_mode(stacb_tree *tree, int mode);

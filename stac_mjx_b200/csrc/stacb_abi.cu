@@ -454,8 +454,13 @@ static int run_pose(const stacb_tree *t, PoseArgs a, cudaStream_t s) {
   if (fits_wide(t)) {  // wide hinge trees: W warps per chain, one chain per CTA (the scheduling mode does not apply)
     const size_t area = ((size_t)2 * t->T.nqp + 7 * (size_t)t->T.pqn) * 4;
     const int grid = std::min(a.C, sms * 8);
+    // more chains than SMs: registers capped for two CTAs per SM.  Pair mode (two groups of W warps per chain, modes 1 / 4) is chosen
+    // automatically for W = 2 only: measured on B200 (tools/wide_pair_probe.py, profiles/mode_sweep_r2f_wide_pair.txt) it is 1.25 x
+    // faster at W = 2, even at W = 4 and slower from W = 6 (the mouse: 689 vs 637 ms) -- both groups share one SM's issue slots and
+    // 384+ threads cap the registers at 168
+    const int wsched = g_force_mode < 0 ? (a.C <= sms ? (t->wide_W == 2 ? 2 : 0) : 1) : (g_force_mode == 4 || g_force_mode == 1 ? 2 : (g_force_mode == 2 ? 1 : 0));
 #define X(w) \
-  if (t->wide_W == w) { CUDA_TRY(launch_wide_pose_##w(t->T, a, grid, area, (g_force_mode < 0 ? a.C > sms : g_force_mode == 2) ? 1 : 0, s)); return STACB_OK; }
+  if (t->wide_W == w) { CUDA_TRY(launch_wide_pose_##w(t->T, a, grid, area, wsched, s)); return STACB_OK; }
     STACB_WIDE_WARPS(X)
 #undef X
   }

@@ -8,8 +8,11 @@
 //     quaternion together (P <- P_a + R(Q_a) P, Q <- Q_a Q) so that a round costs ONE barrier;
 //   * sums over the lanes: the 32-lane butterfly inside every warp, then the warp sums added in warp order;
 //   * wrench prefix: Hillis-Steele inside every warp, then warp w >= 1 adds the totals of the warps before it (summed in warp order);
-// The CPU oracle's mode 2 restates exactly this order (W = 1 reduces to stacb_fast.cuh).  One chain per CTA, frames sequential, the
-// sequential line search of `fast::solve` (no speculation yet): replaces reference stac_mjx/stac_core.py:27-99 for wide trees.
+// The CPU oracle's mode 2 restates exactly this order (W = 1 reduces to stacb_fast.cuh).  One chain per CTA, frames sequential:
+// replaces reference stac_mjx/stac_core.py:27-99 for wide trees.  G = 1: one group of W warps runs the sequential line search of
+// `fast::solve`; G = 2 (few chains): two groups of W warps each share one chain the way the two warps of `fast::solve_pair` do --
+// both line-search candidates at once, then grad f(x+) and the next extrapolation at once -- every evaluation inside its own group
+// (named barrier 1 + group, own WX area), the groups meeting at CTA barriers only to exchange results.  Bit-identical either way.
 #pragma once
 #include "stacb_fast.cuh"
 
@@ -31,15 +34,23 @@ struct WX {  // shared memory of one chain
 };
 
 struct UniW {
-  int t, lane, warp, rounds, free_sa, free_se;
+  int t, lane, warp, grp, rounds, free_sa, free_se;  // t / warp: thread and warp index inside the group
   bool has_free;
   float tol;
   int maxiter, maxls;
   const float *betas;
 };
 
+// barrier of the W warps that share one evaluation: the CTA barrier for G = 1, named barrier 1 + group for G = 2
+template <int W, int G>
+__device__ __forceinline__ void gsync(const UniW &u) {
+  if constexpr (G == 1) __syncthreads();
+  else if (u.grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory");  // (immediate ids: only three barriers are reserved)
+  else asm volatile("bar.sync 2, %0;" ::"n"(32 * W) : "memory");
+}
+
 // sums over all lanes of up to three values at once: one barrier
-template <int W, int NV>
+template <int W, int NV, int G = 1>
 __device__ __forceinline__ void cta_sum(float (&val)[NV], const UniW &u, WX<W> *X, int &par) {
 #pragma unroll
   for (int i = 0; i < NV; i++) val[i] = warp_sum(val[i]);
@@ -47,7 +58,7 @@ __device__ __forceinline__ void cta_sum(float (&val)[NV], const UniW &u, WX<W> *
 #pragma unroll
     for (int i = 0; i < NV; i++) X->red[par][i][u.warp] = val[i];
   }
-  __syncthreads();
+  gsync<W, G>(u);
 #pragma unroll
   for (int i = 0; i < NV; i++) {
     float tot = X->red[par][i][0];
@@ -65,7 +76,7 @@ struct FwdW {
   int qb, vb;  // which halves of the double buffers hold the world poses
 };
 
-template <int W>
+template <int W, int G = 1>
 __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &st, const UniW &u, const float (&pt)[NS], FwdW &S, WX<W> *X, int &par) {
   const int t = u.t;
   // free joint: its seven coordinates and its element live in warp 0 (stacb_tree_create guarantees it), which broadcasts them by
@@ -90,7 +101,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &s
   int b = 0;
   X->q[0][t][0] = Q.w; X->q[0][t][1] = Q.x; X->q[0][t][2] = Q.y; X->q[0][t][3] = Q.z;
   X->v[0][t][0] = v.x; X->v[0][t][1] = v.y; X->v[0][t][2] = v.z;
-  __syncthreads();
+  gsync<W, G>(u);
 #pragma unroll
   for (int r = 0; r < WRT; r++) {
     if (r < u.rounds) {  // uniform
@@ -101,7 +112,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &s
       float *o = X->q[b ^ 1][t], *p = X->v[b ^ 1][t];
       o[0] = Q.w; o[1] = Q.x; o[2] = Q.y; o[3] = Q.z;
       p[0] = v.x; p[1] = v.y; p[2] = v.z;
-      __syncthreads();
+      gsync<W, G>(u);
       b ^= 1;
     }
   }
@@ -119,11 +130,11 @@ __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &s
   S.s = add3(mk3(pa[0], pa[1], pa[2]), rotq(st.off, mk4(qa[0], qa[1], qa[2], qa[3])));
   S.res = mk3((st.kp.x - S.s.x) * st.km.x, (st.kp.y - S.s.y) * st.km.y, (st.kp.z - S.s.z) * st.km.z);
   float e[1] = {fmaf(S.res.z, S.res.z, fmaf(S.res.y, S.res.y, S.res.x * S.res.x))};
-  cta_sum<W, 1>(e, u, X, par);
+  cta_sum<W, 1, G>(e, u, X, par);
   return e[0];
 }
 
-template <int W>
+template <int W, int G = 1>
 __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, const UniW &u, bool free_wanted, float (&g)[NS], WX<W> *X) {
   const float *c0 = X->v[S.vb][0];
   const V3 c = mk3(c0[0], c0[1], c0[2]);
@@ -142,7 +153,7 @@ __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, 
 #pragma unroll
     for (int i = 0; i < 6; i++) X->wsum[u.warp][i] = w[i];
   }
-  __syncthreads();
+  gsync<W, G>(u);
   if (u.warp > 0) {  // warp-uniform
     float off[6];
 #pragma unroll
@@ -156,7 +167,7 @@ __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, 
   }
 #pragma unroll
   for (int i = 0; i < 6; i++) X->wpre[u.t][i] = w[i];
-  __syncthreads();
+  gsync<W, G>(u);
   float wr[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) wr[i] = X->wpre[L.se][i] - X->wpre[L.sa][i];
@@ -272,6 +283,123 @@ __device__ __forceinline__ SolveOut solve(const LaneC<1, WRT> &L, const SiteC &s
   return out;
 }
 
+// fast::solve_pair on two groups of W warps (group g evaluates what warp g evaluates there; same arithmetic, same accepted candidate)
+template <int W>
+struct XPW {  // shared memory
+  float g[32 * W * NS];
+  float acc[2][2], nf[2][2];  // [parity][group]: accepted flag, non-finite loss flag of the two candidates
+  float err, fy;
+};
+
+template <int W>
+__device__ __forceinline__ SolveOut solve_pair_w(const LaneC<1, WRT> &L, const SiteC &st, const UniW &u, const Slots<NS> &co, const float (&q0)[NS],
+                                                 unsigned maskbits, float sqp, float (&x)[NS], WX<W> *X, XPW<W> *xc, int &par, int &xpar) {
+  constexpr int G = 2;
+  float y[NS], g[NS], gt[NS], xj[NS], d[NS];
+#pragma unroll
+  for (int m = 0; m < NS; m++) { x[m] = q0[m]; y[m] = x[m]; g[m] = 0.f; }
+  SolveOut out;
+  out.iters = 0; out.ls = 0; out.bad = false; out.err = __int_as_float(0x7f800000);
+  if (u.maxiter <= 0) return out;
+  const bool fw = u.has_free && __syncthreads_or(u.t < 7 && ((maskbits >> 1) & 1u));
+  SolveC<NS> sc;
+  {
+    const float inf = __int_as_float(0x7f800000);
+    float dn[NS];
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+      const bool bit = (maskbits >> m) & 1u, frozen = co.valid[m] && !bit;
+      sc.gm[m] = bit ? 1.0f : 0.0f;
+      sc.lb[m] = frozen ? -inf : co.lb[m];
+      sc.ub[m] = frozen ? inf : co.ub[m];
+      dn[m] = frozen ? clipm(q0[m], co.lb[m], co.ub[m]) - q0[m] : 0.0f;
+    }
+    float v[1] = {fast::lane_dot<NS>(dn, dn)};
+    cta_sum<W, 1, G>(v, u, X, par);
+    sqp = v[0] + sqp;
+  }
+  FwdW S;
+  float fy = eval_fwd<W, G>(L, st, u, y, S, X, par);  // f(y0), grad f(y0): both groups (identical values)
+  eval_bwd<W, G>(L, S, u, fw, g, X);
+#pragma unroll
+  for (int m = 0; m < NS; m++) g[m] = g[m] * sc.gm[m];
+  float t = 1.0f, stp = 1.0f;
+  int base = 0;
+  const int w = u.grp;
+  for (;;) {
+    // phase A: this group's line-search candidate
+    const float sj = w ? stp * 0.5f : stp;
+#pragma unroll
+    for (int m = 0; m < NS; m++) {
+      xj[m] = clipm(fmaf(-sj, g[m], y[m]), sc.lb[m], sc.ub[m]);
+      d[m] = xj[m] - y[m];
+    }
+    float v2[2] = {fast::lane_dot<NS>(d, d), fast::lane_dot<NS>(d, g)};
+    cta_sum<W, 2, G>(v2, u, X, par);
+    const float sq = v2[0] + sqp, dg = v2[1];
+    const float f = eval_fwd<W, G>(L, st, u, xj, S, X, par);
+    const float dec = sj * (f - fy);
+    const float cond = fmaf(sj, dg, 0.5f * sq);
+    const bool rejected = (dec > cond + 1.1920929e-07f) && (base + w < u.maxls);
+    if (u.t == 0) {
+      xc->acc[xpar][w] = rejected ? 0.f : 1.f;
+      xc->nf[xpar][w] = (f - f == 0.0f) ? 0.f : 1.f;
+    }
+    __syncthreads();
+    const bool a0 = xc->acc[xpar][0] != 0.f, a1 = xc->acc[xpar][1] != 0.f;
+    const int k = a0 ? 0 : (a1 ? 1 : -1);
+    if (xc->nf[xpar][0] != 0.f || (k != 0 && xc->nf[xpar][1] != 0.f)) out.bad = true;  // candidates the sequential search evaluates
+    xpar ^= 1;
+    if (k < 0) {  // both rejected: next two step sizes
+      base += 2;
+      stp = stp * 0.25f;
+      continue;
+    }
+    out.ls += base + k + 1;
+    const float sk = k ? stp * 0.5f : stp;
+    const float beta = beta_of(u.betas, out.iters, t);
+    // phase B
+    if (w == k) {  // gradient at the accepted x+ (this group's forward state) -> unit-step fixed-point residual
+      eval_bwd<W, G>(L, S, u, fw, gt, X);
+#pragma unroll
+      for (int m = 0; m < NS; m++) {
+        gt[m] = gt[m] * sc.gm[m];
+        d[m] = clipm(xj[m] - gt[m], sc.lb[m], sc.ub[m]) - xj[m];
+      }
+      float v[1] = {fast::lane_dot<NS>(d, d)};
+      cta_sum<W, 1, G>(v, u, X, par);
+      if (u.t == 0) xc->err = sqrtf(v[0]);
+#pragma unroll
+      for (int m = 0; m < NS; m++) { y[m] = fmaf(beta, xj[m] - x[m], xj[m]); x[m] = xj[m]; }
+    } else {  // the partner: x+_k, the extrapolation y', f(y') and grad f(y')
+#pragma unroll
+      for (int m = 0; m < NS; m++) {
+        const float xk = clipm(fmaf(-sk, g[m], y[m]), sc.lb[m], sc.ub[m]);
+        y[m] = fmaf(beta, xk - x[m], xk);
+        x[m] = xk;
+      }
+      const float fyn = eval_fwd<W, G>(L, st, u, y, S, X, par);
+      eval_bwd<W, G>(L, S, u, fw, gt, X);
+#pragma unroll
+      for (int m = 0; m < NS; m++) xc->g[32 * W * m + u.t] = gt[m] * sc.gm[m];
+      if (u.t == 0) xc->fy = fyn;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < NS; m++) g[m] = xc->g[32 * W * m + u.t];
+    fy = xc->fy;
+    out.err = xc->err;
+    stp = (sk <= 1e-6f) ? 1.0f : sk / 0.5f;
+    out.iters++;
+    sqp = 0.f;
+    base = 0;
+    // no third barrier: g / fy / err are written again only after the NEXT phase-A barrier, which a thread reaches only once it has
+    // read this iteration's values; the accept flags alternate between two parities
+    if (!(out.err > u.tol && out.iters < u.maxiter)) break;
+  }
+  return out;
+}
+
 __device__ __forceinline__ void slots_init_w(Slots<NS> &co, SlotAdr<1> &sa, const LaneC<1, WRT> &L, const DevTree &T, int t, const float *__restrict__ lb,
                                              const float *__restrict__ ub) {
   co.valid[0] = L.hinge[0]; sa.adr[0] = L.adr[0];
@@ -284,7 +412,7 @@ __device__ __forceinline__ void slots_init_w(Slots<NS> &co, SlotAdr<1> &sa, cons
   }
 }
 
-template <int W>
+template <int W, int G = 1>
 __device__ __forceinline__ float passive_sq_w(const DevTree &T, const UniW &u, const float *q, const float *__restrict__ lb, const float *__restrict__ ub,
                                               WX<W> *X, int &par) {
   float acc = 0.f;
@@ -297,24 +425,27 @@ __device__ __forceinline__ float passive_sq_w(const DevTree &T, const UniW &u, c
     first = false;
   }
   float v[1] = {acc};
-  cta_sum<W, 1>(v, u, X, par);
+  cta_sum<W, 1, G>(v, u, X, par);
   return v[0];
 }
 
-// One chain per CTA of W warps; frames sequential; the stage loop of fast::fast_pose_kernel.
+// One chain per CTA of G groups of W warps; frames sequential; the stage loop of fast::fast_pose_kernel.
 // MINB: CTAs per SM the registers are capped for (2 once there are more chains than SMs and two CTAs fit the register file)
-template <int W, int NBF, int MINB>
-__global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, PoseArgs a) {
+// G = 2: pair mode (solve_pair_w) -- both groups carry the whole solver state; group 0 stages and writes.
+template <int W, int NBF, int MINB, int G>
+__global__ void __launch_bounds__(32 * W * G, MINB) wide_pose_kernel(DevTree T, PoseArgs a) {
   extern __shared__ float smem[];
   __shared__ int s_chain;
   __shared__ float s_beta[BT + 1];
   if (threadIdx.x == 0) beta_table_init(s_beta);
   __syncthreads();
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, idl = 32 * W - 1;
+  constexpr int NT = 32 * W * G;  // threads of the CTA (staging loops); a group has 32 W
+  const int tc = threadIdx.x, grp = tc / (32 * W), t = tc - grp * (32 * W), lane = t & 31, warp = t >> 5, idl = 32 * W - 1;
   const int area = 2 * T.nqp + 7 * T.pqn;  // qbuf [nqp], (unused) [nqp], PQ [7 pqn]: the cold full-model FK of the outputs (warp 0)
   Chain ch(T, smem, nullptr, lane, 0, 1, 0);
-  WX<W> *X = reinterpret_cast<WX<W> *>(smem + area);
-  const bool writer = warp == 0;
+  WX<W> *X = reinterpret_cast<WX<W> *>(smem + area) + grp;
+  XPW<W> *xc = reinterpret_cast<XPW<W> *>(reinterpret_cast<WX<W> *>(smem + area) + G);
+  const bool writer = warp == 0 && grp == 0;
   LaneC<1, WRT> L;
   lane_init<1, WRT>(L, T, t, idl);
   SiteC st;
@@ -323,7 +454,7 @@ __global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, Pose
   SlotAdr<1> sa;
   slots_init_w(co, sa, L, T, t, a.lb, a.ub);
   UniW u;
-  u.t = t; u.lane = lane; u.warp = warp; u.rounds = T.fs.rounds; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.fs_free_e >= 0;
+  u.t = t; u.lane = lane; u.warp = warp; u.grp = grp; u.rounds = T.fs.rounds; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.fs_free_e >= 0;
   u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls; u.betas = s_beta;
   const int nq = T.nq, K = T.K, nb = T.nbody, S1 = 1 + a.P, npassive = T.npassive;
   const MaskSpec full_ms = {nullptr, nq}, root_ms = {nullptr, a.root_dims};
@@ -331,13 +462,13 @@ __global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, Pose
   const int n_root = a.do_root ? 2 : 0;
   const int n_pose = (a.do_root == 2) ? 0 : a.F;
   const int n_stage = n_root + n_pose * S1;
-  int par = 0;
+  int par = 0, xpar = 0;
   for (;;) {
     if (threadIdx.x == 0) s_chain = atomicAdd(a.counter, 1);
     __syncthreads();
     const int c = s_chain;
     if (c >= a.C) break;
-    for (int i = t; i < nq; i += 32 * W) ch.qbuf[i] = a.qpos_io[(size_t)c * nq + i];
+    for (int i = tc; i < nq; i += NT) ch.qbuf[i] = a.qpos_io[(size_t)c * nq + i];
     __syncthreads();
     float q[NS], q0[NS], x[NS];
     slots_gather<1>(co, sa, ch.qbuf, q);
@@ -364,25 +495,27 @@ __global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, Pose
         q0[m] = q[m];
         if (is_root && co.valid[m] && sa.adr[m] < 3) q0[m] = kpc[3 * a.root_kp_idx + sa.adr[m]];
       }
-      const float sqp = npassive ? passive_sq_w<W>(T, u, ch.qbuf, a.lb, a.ub, X, par) : 0.f;
-      const SolveOut so = solve<W>(L, st, u, co, q0, bits, sqp, x, X, par);
+      const float sqp = npassive ? passive_sq_w<W, G>(T, u, ch.qbuf, a.lb, a.ub, X, par) : 0.f;
+      SolveOut so;
+      if constexpr (G == 2) so = solve_pair_w<W>(L, st, u, co, q0, bits, sqp, x, X, xc, par, xpar);
+      else so = solve<W>(L, st, u, co, q0, bits, sqp, x, X, par);
 #pragma unroll
       for (int m = 0; m < NS; m++) q[m] = ((bits >> m) & 1u) ? x[m] : q0[m];
       bad |= so.bad;
       if (npassive && u.maxiter > 0) {
-        for (int i = t; i < npassive; i += 32 * W) {
+        for (int i = tc; i < npassive; i += NT) {
           const int p = __ldg(T.passive + i);
           if (mask_has(ms, p)) ch.qbuf[p] = clipm(ch.qbuf[p], a.lb[p], a.ub[p]);
         }
         __syncthreads();
       }
       if (is_root) {
-        if (a.root_stats && t == 0) { a.root_stats[4 * c + 2 * sidx] = so.iters; a.root_stats[4 * c + 2 * sidx + 1] = so.ls; }
+        if (a.root_stats && tc == 0) { a.root_stats[4 * c + 2 * sidx] = so.iters; a.root_stats[4 * c + 2 * sidx + 1] = so.ls; }
       } else {
         const size_t fi = (size_t)c * a.F + f;
-        if (a.iters && t == 0) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
+        if (a.iters && tc == 0) { a.iters[fi * S1 + sg] = so.iters; a.ls_evals[fi * S1 + sg] = so.ls; }
         if (sg == a.P) {  // last solve of the frame: full-model FK of the raw solution -> outputs (warp 0)
-          slots_scatter<1>(co, sa, q, ch.qbuf);
+          if (grp == 0) slots_scatter<1>(co, sa, q, ch.qbuf);
           __syncthreads();
           if (writer) {
             outputs_from_qbuf<NBF>(ch, st, a.site_pos, a.qpos ? a.qpos + fi * nq : nullptr, a.xpos ? a.xpos + fi * nb * 3 : nullptr,
@@ -390,7 +523,7 @@ __global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, Pose
             if (a.err && lane == 0) a.err[fi] = so.err;
           }
           __syncthreads();
-          if (a.sites && st.k >= 0) {  // every site thread writes its own site from the cold FK's poses (same arithmetic as outputs_from_qbuf)
+          if (a.sites && st.k >= 0 && grp == 0) {  // every site thread writes its own site from the cold FK's poses (same arithmetic as outputs_from_qbuf)
             const float *o = ch.PQ + 7 * st.ef;
             const V3 off = mk3(__ldg(a.site_pos + 3 * st.k), __ldg(a.site_pos + 3 * st.k + 1), __ldg(a.site_pos + 3 * st.k + 2));
             const V3 sp = add3(lds3(o), rotate(off, lds4(o + 3)));
@@ -402,10 +535,10 @@ __global__ void __launch_bounds__(32 * W, MINB) wide_pose_kernel(DevTree T, Pose
       }
       if (warp == 0) normalize_free<1>(Uni{lane, 0, u.has_free, 0.f, 0, 0, nullptr}, q);  // threads 0..6 hold the free joint
     }
-    slots_scatter<1>(co, sa, q, ch.qbuf);
+    if (grp == 0) slots_scatter<1>(co, sa, q, ch.qbuf);
     __syncthreads();
-    for (int i = t; i < nq; i += 32 * W) a.qpos_io[(size_t)c * nq + i] = ch.qbuf[i];
-    if (a.status && t == 0) a.status[c] = bad ? 1 : 0;
+    for (int i = tc; i < nq; i += NT) a.qpos_io[(size_t)c * nq + i] = ch.qbuf[i];
+    if (a.status && tc == 0) a.status[c] = bad ? 1 : 0;
     __syncthreads();
   }
 }

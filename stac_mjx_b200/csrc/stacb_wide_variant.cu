@@ -6,14 +6,19 @@ namespace stacb {
 #define FN_(prefix, a) prefix##a
 #define FN(prefix, a) FN_(prefix, a)
 
-cudaError_t FN(launch_wide_pose_, V_WW)(const DevTree &T, const PoseArgs &a, int grid, size_t area_bytes, int dense, cudaStream_t s) {
-  auto k = (dense && V_WW <= 6) ? wide::wide_pose_kernel<V_WW, 8, (V_WW <= 6 ? 2 : 1)> : wide::wide_pose_kernel<V_WW, 8, 1>;
-  const size_t smem = area_bytes + sizeof(wide::WX<V_WW>);
+// sched: 0 one group of W warps per chain, 1 the same with registers capped for two CTAs per SM (W <= 6), 2 pair mode (two groups
+// of W warps per chain, W <= 8: 512 threads)
+cudaError_t FN(launch_wide_pose_, V_WW)(const DevTree &T, const PoseArgs &a, int grid, size_t area_bytes, int sched, cudaStream_t s) {
+  auto k = wide::wide_pose_kernel<V_WW, 8, 1, 1>;
+  int groups = 1;
+  if (sched == 1 && V_WW <= 6) k = wide::wide_pose_kernel<V_WW, 8, (V_WW <= 6 ? 2 : 1), 1>;
+  if (sched == 2) { k = wide::wide_pose_kernel<V_WW, 8, 1, 2>; groups = 2; }
+  const size_t smem = area_bytes + groups * sizeof(wide::WX<V_WW>) + (groups == 2 ? sizeof(wide::XPW<V_WW>) : 0);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<grid, 32 * V_WW, smem, s>>>(T, a);
+  k<<<grid, 32 * V_WW * groups, smem, s>>>(T, a);
   return cudaGetLastError();
 }
 

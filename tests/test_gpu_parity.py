@@ -590,7 +590,8 @@ def test_random_trees_with_welded_bodies_on_the_register_resident_path(seed):
 @pytest.mark.parametrize("seed,n_bodies,n_sites,p_welded", [(21, 70, 20, 0.1), (22, 140, 40, 0.1), (23, 250, 60, 0.1), (25, 250, 140, 0.02), (26, 254, 160, 0.0)])
 def test_random_wide_trees_on_the_multi_warp_path(seed, n_bodies, n_sites, p_welded):
     """Random single-hinge trees of 34 .. 200+ jointed elements: the multi-warp register-resident kernels (2, 4, 6, 8 warps per
-    chain) against oracle mode 2, bit for bit -- loss / gradient, masked solves, a clip with root optimisation, both register caps."""
+    chain) against oracle mode 2, bit for bit -- loss / gradient, masked solves, a clip with root optimisation, both register caps and
+    the pair mode (two groups of W warps per chain)."""
     from oracle.oracle import Oracle
     from random_trees import random_tree
     from stac_mjx_b200.engine import Engine
@@ -622,7 +623,7 @@ def test_random_wide_trees_on_the_multi_warp_path(seed, n_bodies, n_sites, p_wel
     kpc = kp.reshape(2, 2, -1)
     kw = dict(do_root=1, root_kp_idx=0, trunk_kps=np.ones(K, bool), tol=1e-5, maxiter=30)
     ref = o.pose_clips(kpc, t.qpos0, off, lb, ub, part[None], **kw)
-    for mode in (0, 2):
+    for mode in (0, 2, 4, -1):  # one group of W warps, the same with capped registers, pair mode (two groups), auto (= pair for few chains)
         eng.set_mode(mode)
         qio = torch.tensor(np.tile(t.qpos0.astype(np.float32), (2, 1)), device=eng.device)
         out = eng.pose_clips(kpc, qio, off, lb, ub, part[None], **kw)
