@@ -86,6 +86,38 @@ def test_fit_offsets_matches_oracle_driven_restatement(rodent):
     assert d.qpos.shape == (F, rodent.tree.nq) and d.xpos.shape == (F, rodent.tree.nbody, 3)
 
 
+def test_fit_offsets_with_a_frame_sample_matches_the_oracle_on_the_same_frames(rodent):
+    """BASELINE config 3's shape scaled down (the rodent config samples 100 of 1000 fit frames; here 12 of 40): the m-phase runs on
+    the frames jax.random.permutation(PRNGKey(0), arange(F))[:n] selects (compute_stac.py:134-140, reproduced in jax_random.py),
+    in the sample's own order; the oracle-driven restatement uses the same indices."""
+    from stac_mjx_b200 import compute_stac
+
+    F, n_iters, n_sample = 40, 2, 12
+    st = make_stac(rodent, F, n_iters=n_iters)
+    st.cfg.model.N_SAMPLE_FRAMES = n_sample
+    s, o = rodent.setup, rodent.oracle(np.float32, 2)
+    kp, _, _ = rodent.session(F, F, seed=78)
+    d = st.fit_offsets(kp)
+    tidx = compute_stac.sample_time_indices(F, n_sample)
+    assert len(tidx) == n_sample and len(set(tidx.tolist())) == n_sample and not np.array_equal(tidx, np.sort(tidx))
+    offs = s.initial_offsets.copy()
+    kw = rodent.root_kw()
+    q = _root_only(o, kp, rodent.tree.qpos0.astype(np.float32), offs, s, kw)
+    for _ in range(n_iters):
+        r = o.pose_clips(kp[None], q, offs, s.lb, s.ub, s.indiv_parts, **{**kw, "do_root": 0})
+        q = r["qpos"][0, -1]
+        offs, _ = o.m_opt(kp[tidx], r["qpos"][0][tidx], offs, s.is_regularized, float(rodent.cfg.model.M_REG_COEF))
+    r = o.pose_clips(kp[None], q, offs, s.lb, s.ub, s.indiv_parts, **{**kw, "do_root": 0})
+    np.testing.assert_allclose(d.offsets, offs, atol=2e-5, rtol=0)
+    # a fit on all frames gives different offsets: the sample matters, so agreement above is evidence for the indices
+    st_all = make_stac(rodent, F, n_iters=n_iters)
+    st_all.cfg.model.N_SAMPLE_FRAMES = F
+    assert np.abs(st_all.fit_offsets(kp).offsets - d.offsets).max() > 1e-4
+    resid_gpu = np.linalg.norm(d.marker_sites - kp.reshape(F, -1, 3), axis=-1)
+    resid_ref = np.linalg.norm(r["sites"][0] - kp.reshape(F, -1, 3), axis=-1)
+    assert abs(resid_gpu.mean() - resid_ref.mean()) < 1e-4
+
+
 def _root_only(o, kp, q, offs, s, kw):
     # root_optimization (compute_stac.py:17-104) spelled out on the oracle's single-solve entry point
     nq = len(q)
