@@ -170,13 +170,44 @@ __global__ void __launch_bounds__(256) tput_kernel(float *out, int iters, float 
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) s += a[i];
+  } else if (MODE == 4) {  // SHFL throughput: 8 independent values, one indexed shuffle each per iteration
+    float a[8];
+    const int src = (threadIdx.x * 7 + 3) & 31;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = __shfl_sync(0xffffffffu, a[i], src);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+  } else if (MODE == 5) {  // the solver's mix: per 8 SHFL, 56 FP32 instructions (12.5 % shuffles)
+    float a[8], v[8];
+    const int src = (threadIdx.x * 7 + 3) & 31;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = 1.0f + 1e-3f * (threadIdx.x + i); v[i] = 0.5f + 1e-3f * i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float t = __shfl_sync(0xffffffffu, a[i], src);
+        v[i] = fmaf(v[i], b, t);
+        v[i] = v[i] * b;
+        v[i] = v[i] + c;
+        v[i] = fmaf(v[i], b, c);
+        v[i] = fmaf(v[i], t, c);
+        v[i] = v[i] * t;
+        a[i] = fmaf(v[i], b, c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i] + v[i];
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 template <int MODE>
-static void run_tput(const char *name, float *out, int sms, double flop_per_thread_iter) {
-  const int blocks = sms * 8, threads = 256, iters = 20000;
+static void run_tput(const char *name, float *out, int sms, double flop_per_thread_iter, int blocks_per_sm = 8, double instr_per_thread_iter = 0, int clk_khz = 0) {
+  const int blocks = sms * blocks_per_sm, threads = 256, iters = 20000;
   tput_kernel<MODE><<<blocks, threads>>>(out, 200, 0.9999f, 1e-4f);
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
@@ -190,7 +221,11 @@ static void run_tput(const char *name, float *out, int sms, double flop_per_thre
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
   }
-  printf("tput %-28s %8.2f TFLOP/s  (%.3f ms)\n", name, flop_per_thread_iter * iters * (double)blocks * threads / (best * 1e-3) / 1e12, best);
+  if (instr_per_thread_iter > 0)  // warp instructions per clock per SM
+    printf("tput %-28s %8.3f warp-instr/clk/SM at %d warps/SM (%.3f ms)\n", name,
+           instr_per_thread_iter * iters * (double)blocks * threads / 32.0 / (best * 1e-3) / (clk_khz * 1e3) / sms, blocks_per_sm * threads / 32, best);
+  else
+    printf("tput %-28s %8.2f TFLOP/s  (%.3f ms)\n", name, flop_per_thread_iter * iters * (double)blocks * threads / (best * 1e-3) / 1e12, best);
 }
 
 int main() {
@@ -218,5 +253,7 @@ int main() {
   run_tput<1>("FFMA reg,imm,imm", out, sms, 32.0);
   run_tput<2>("FFMA2 packed", out, sms, 32.0);
   run_tput<3>("FFMA/FMUL/FADD mix", out, sms, 24.0);  // 4 groups x (2 fma + mul + add) = 24 flop
+  for (int bps = 1; bps <= 8; bps *= 2) run_tput<4>("SHFL (indexed)", out, sms, 0, bps, 8.0, clk);
+  for (int bps = 1; bps <= 2; bps *= 2) run_tput<5>("8 SHFL + 56 FP32 (all instr)", out, sms, 0, bps, 64.0, clk);
   return 0;
 }
