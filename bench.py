@@ -131,7 +131,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -470,14 +470,34 @@ def run_ours(args):
             "clocks": sampler.summary(),
             **extra,
         }  # fmt: skip
-        print(json.dumps(line), flush=True)
+        emit(line)
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: route file descriptor 1 to stderr for everything else -- libraries print there too
+    (NCCL writes its version banner to fd 1 when NCCL_DEBUG is set) -- and keep the original for `emit`."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
