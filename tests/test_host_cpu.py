@@ -222,6 +222,47 @@ def test_real_mocap_fixture_is_what_load_data_produces(tmp_path):
     np.testing.assert_allclose(out, g["kp"][:20], rtol=1e-6, atol=1e-9)
 
 
+def test_load_data_keypoint_name_errors_and_label3d_names(tmp_path):
+    """reference tests/unit/test_utils.py:48-80: names from a label3d file, no names at all, fewer names than keypoints."""
+    import scipy.io as spio
+
+    from conftest import get_case
+    from stac_mjx_b200.config import Cfg
+
+    c = get_case("rodent")
+    names_mocap = list(c.cfg.model.KP_NAMES)
+    K = len(names_mocap)
+    rng = np.random.default_rng(3)
+    pred = rng.normal(size=(7, 3, K))
+    spio.savemat(tmp_path / "m.mat", {"pred": pred})
+    spio.savemat(tmp_path / "names.mat", {"joint_names": np.array([[n] for n in names_mocap], dtype=object)})
+
+    def cfg_with(**model):
+        d = c.cfg.to_dict()
+        d["stac"]["data_path"] = "m.mat"
+        for k, v in model.items():
+            if v is None:
+                d["model"].pop(k, None)
+            else:
+                d["model"][k] = v
+        return Cfg(d)
+
+    base, names0 = io.load_data(cfg_with(), base_path=tmp_path)
+    assert base.shape == (7, 3 * K) and len(names0) == K
+    # keypoint names read from the label3d file instead of the config
+    out, names = io.load_data(cfg_with(KP_NAMES=None, KP_NAMES_LABEL3D_PATH=str(tmp_path / "names.mat")), base_path=tmp_path)
+    assert names == names0
+    np.testing.assert_array_equal(out, base)
+    with pytest.raises(ValueError, match="Keypoint names not provided"):
+        io.load_data(cfg_with(KP_NAMES=None), base_path=tmp_path)
+    with pytest.raises(ValueError, match="is not the same as the number of keypoints"):
+        io.load_data(cfg_with(KP_NAMES=names_mocap[:-2]), base_path=tmp_path)
+    bad = cfg_with()
+    bad.stac.data_path = "m.csv"
+    with pytest.raises(ValueError, match="Unsupported file extension"):
+        io.load_data(bad, base_path=tmp_path)
+
+
 def test_package_data_unbatched():
     # reference tests/unit/test_stac_package.py:11-38
     from stac_mjx_b200.stac import Stac
