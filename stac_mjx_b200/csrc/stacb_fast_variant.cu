@@ -10,7 +10,7 @@ namespace stacb {
 
 template <class K>
 static cudaError_t launch(K k, const DevTree &T, const PoseArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // dynamic + static (momentum table, counters: ~2 KB) beyond the 48 KB default needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

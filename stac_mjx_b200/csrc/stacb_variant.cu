@@ -17,7 +17,7 @@ cudaError_t FN(launch_pose_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T, 
          : coop == 2 ? pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 2>
          : (coop == 3 && V_NB > 1) ? pose_clips_kernel<V_CPL, (V_NB > 1 ? NBG : V_NB), V_NBF, V_SPL, (V_NB > 1 ? 3 : 0)>
                                    : pose_clips_kernel<V_CPL, V_NB, V_NBF, V_SPL, 0>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // dynamic + static (momentum table, counters: ~2 KB) beyond the 48 KB default needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
@@ -27,7 +27,7 @@ cudaError_t FN(launch_pose_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T, 
 
 cudaError_t FN(launch_batch_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T, const BatchArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
   auto k = batch_kernel<V_CPL, V_NB, V_NBF, V_SPL>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // dynamic + static (momentum table, counters: ~2 KB) beyond the 48 KB default needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
@@ -37,7 +37,7 @@ cudaError_t FN(launch_batch_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T,
 
 cudaError_t FN(launch_mphase_, V_CPL, V_NB, V_NBF, V_SPL, V_JM)(const DevTree &T, const MArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
   auto k = m_phase_kernel<V_CPL, V_NB, V_NBF, V_SPL>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // dynamic + static (momentum table, counters: ~2 KB) beyond the 48 KB default needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

@@ -25,13 +25,15 @@ constexpr int WRT = 8;  // pointer-jumping rounds a lane can hold (tree depth <=
 constexpr int NS = 2;   // solver slots per thread: the element's hinge, a free-joint coordinate (threads 0..6)
 
 template <int W>
-struct WX {  // shared memory of one chain
-  float q[2][32 * W][4];  // pointer jumping of the world quaternions (double buffer); q[qb] holds them after the forward pass
-  float v[2][32 * W][3];  // ... of the world positions; v[vb]
-  float red[2][3][W];     // warp partials of the sums over all lanes ([parity][value][warp])
-  float wsum[W][6];       // warp totals of the wrench scan
-  float wpre[32 * W][6];  // inclusive wrench prefix by lane
+struct WX {  // shared memory of one chain (16-byte aligned: poses and prefixes move as 128-bit shared-memory accesses)
+  float4 q[2][32 * W];     // pointer jumping of the world quaternions (double buffer; w, x, y, z); q[qb] holds them after the forward pass
+  float4 v[2][32 * W];     // ... of the world positions (x, y, z, unused); v[vb]
+  float4 wpre[32 * W][2];  // inclusive wrench prefix by lane (six values, two unused)
+  float red[2][3][W];      // warp partials of the sums over all lanes ([parity][value][warp])
+  float wsum[W][6];        // warp totals of the wrench scan
 };
+__device__ __forceinline__ Q4 q4_of(const float4 a) { return mk4(a.x, a.y, a.z, a.w); }
+__device__ __forceinline__ V3 v3_of(const float4 a) { return mk3(a.x, a.y, a.z); }
 
 struct UniW {
   int t, lane, warp, grp, rounds, free_sa, free_se;  // t / warp: thread and warp index inside the group
@@ -99,35 +101,30 @@ __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &s
   // world poses: pointer jumping of position and quaternion TOGETHER through shared memory, one barrier per round
   // (P <- P_a + R(Q_a) P, Q <- Q_a Q with the ancestor a at distance 2^r; the one-warp path jumps them separately by shuffles)
   int b = 0;
-  X->q[0][t][0] = Q.w; X->q[0][t][1] = Q.x; X->q[0][t][2] = Q.y; X->q[0][t][3] = Q.z;
-  X->v[0][t][0] = v.x; X->v[0][t][1] = v.y; X->v[0][t][2] = v.z;
+  X->q[0][t] = make_float4(Q.w, Q.x, Q.y, Q.z);
+  X->v[0][t] = make_float4(v.x, v.y, v.z, 0.f);
   gsync<W, G>(u);
 #pragma unroll
   for (int r = 0; r < WRT; r++) {
     if (r < u.rounds) {  // uniform
-      const float *qa = X->q[b][L.src[r]], *pa = X->v[b][L.src[r]];
-      const Q4 Qa = mk4(qa[0], qa[1], qa[2], qa[3]);
-      v = add3(mk3(pa[0], pa[1], pa[2]), rotq(v, Qa));
+      const Q4 Qa = q4_of(X->q[b][L.src[r]]);
+      const V3 Pa = v3_of(X->v[b][L.src[r]]);
+      v = add3(Pa, rotq(v, Qa));
       Q = qmul(Qa, Q);
-      float *o = X->q[b ^ 1][t], *p = X->v[b ^ 1][t];
-      o[0] = Q.w; o[1] = Q.x; o[2] = Q.y; o[3] = Q.z;
-      p[0] = v.x; p[1] = v.y; p[2] = v.z;
+      X->q[b ^ 1][t] = make_float4(Q.w, Q.x, Q.y, Q.z);
+      X->v[b ^ 1][t] = make_float4(v.x, v.y, v.z, 0.f);
       gsync<W, G>(u);
       b ^= 1;
     }
   }
-  {
-    const float *a = X->q[b][L.par];
-    S.Qp = mk4(a[0], a[1], a[2], a[3]);
-  }
+  S.Qp = q4_of(X->q[b][L.par]);
   S.Q = Q;
   S.P = v;
   S.qb = b;
   S.vb = b;
   const int c = b;
   // marker sites, masked residuals, loss
-  const float *pa = X->v[c][st.eb], *qa = X->q[b][st.eb];
-  S.s = add3(mk3(pa[0], pa[1], pa[2]), rotq(st.off, mk4(qa[0], qa[1], qa[2], qa[3])));
+  S.s = add3(v3_of(X->v[c][st.eb]), rotq(st.off, q4_of(X->q[b][st.eb])));
   S.res = mk3((st.kp.x - S.s.x) * st.km.x, (st.kp.y - S.s.y) * st.km.y, (st.kp.z - S.s.z) * st.km.z);
   float e[1] = {fmaf(S.res.z, S.res.z, fmaf(S.res.y, S.res.y, S.res.x * S.res.x))};
   cta_sum<W, 1, G>(e, u, X, par);
@@ -136,8 +133,7 @@ __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &s
 
 template <int W, int G = 1>
 __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, const UniW &u, bool free_wanted, float (&g)[NS], WX<W> *X) {
-  const float *c0 = X->v[S.vb][0];
-  const V3 c = mk3(c0[0], c0[1], c0[2]);
+  const V3 c = v3_of(X->v[S.vb][0]);
   const V3 f = mk3(-2.0f * S.res.x, -2.0f * S.res.y, -2.0f * S.res.z);
   const V3 tq = cross3(sub3(S.s, c), f);
   float w[6] = {f.x, f.y, f.z, tq.x, tq.y, tq.z};
@@ -165,15 +161,16 @@ __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, 
 #pragma unroll
     for (int i = 0; i < 6; i++) w[i] = w[i] + off[i];
   }
-#pragma unroll
-  for (int i = 0; i < 6; i++) X->wpre[u.t][i] = w[i];
+  X->wpre[u.t][0] = make_float4(w[0], w[1], w[2], w[3]);
+  X->wpre[u.t][1] = make_float4(w[4], w[5], 0.f, 0.f);
   gsync<W, G>(u);
   float wr[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) wr[i] = X->wpre[L.se][i] - X->wpre[L.sa][i];
+  {
+    const float4 e0 = X->wpre[L.se][0], e1 = X->wpre[L.se][1], a0 = X->wpre[L.sa][0], a1 = X->wpre[L.sa][1];
+    wr[0] = e0.x - a0.x; wr[1] = e0.y - a0.y; wr[2] = e0.z - a0.z; wr[3] = e0.w - a0.w; wr[4] = e1.x - a1.x; wr[5] = e1.y - a1.y;
+  }
   const V3 F = mk3(wr[0], wr[1], wr[2]), Tq = mk3(wr[3], wr[4], wr[5]);
-  const float *pa = X->v[S.vb][L.par];
-  const V3 pp = mk3(pa[0], pa[1], pa[2]);
+  const V3 pp = v3_of(X->v[S.vb][L.par]);
   const Q4 pc = conj4(S.Qp);
   const V3 T0 = sub3(Tq, cross3(sub3(pp, c), F));
   const V3 Fp = rotq(F, pc), Tp = rotq(T0, pc);
@@ -181,8 +178,10 @@ __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, 
   g[1] = 0.f;
   if (free_wanted) {  // uniform; the free joint's subtree is its body's subtree: the same two prefix entries
     float wf[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) wf[i] = X->wpre[u.free_se][i] - X->wpre[u.free_sa][i];
+    {
+      const float4 e0 = X->wpre[u.free_se][0], e1 = X->wpre[u.free_se][1], a0 = X->wpre[u.free_sa][0], a1 = X->wpre[u.free_sa][1];
+      wf[0] = e0.x - a0.x; wf[1] = e0.y - a0.y; wf[2] = e0.z - a0.z; wf[3] = e0.w - a0.w; wf[4] = e1.x - a1.x; wf[5] = e1.y - a1.y;
+    }
     const V3 Ff = mk3(wf[0], wf[1], wf[2]);
     const V3 Tf = sub3(mk3(wf[3], wf[4], wf[5]), cross3(sub3(S.fpos, c), Ff));
     float g4[4];
@@ -434,7 +433,7 @@ __device__ __forceinline__ float passive_sq_w(const DevTree &T, const UniW &u, c
 // G = 2: pair mode (solve_pair_w) -- both groups carry the whole solver state; group 0 stages and writes.
 template <int W, int NBF, int MINB, int G>
 __global__ void __launch_bounds__(32 * W * G, MINB) wide_pose_kernel(DevTree T, PoseArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   __shared__ int s_chain;
   __shared__ float s_beta[BT + 1];
   if (threadIdx.x == 0) beta_table_init(s_beta);
@@ -443,8 +442,9 @@ __global__ void __launch_bounds__(32 * W * G, MINB) wide_pose_kernel(DevTree T, 
   const int tc = threadIdx.x, grp = tc / (32 * W), t = tc - grp * (32 * W), lane = t & 31, warp = t >> 5, idl = 32 * W - 1;
   const int area = 2 * T.nqp + 7 * T.pqn;  // qbuf [nqp], (unused) [nqp], PQ [7 pqn]: the cold full-model FK of the outputs (warp 0)
   Chain ch(T, smem, nullptr, lane, 0, 1, 0);
-  WX<W> *X = reinterpret_cast<WX<W> *>(smem + area) + grp;
-  XPW<W> *xc = reinterpret_cast<XPW<W> *>(reinterpret_cast<WX<W> *>(smem + area) + G);
+  const int xoff = (area + 3) & ~3;  // the exchange areas start on a 16-byte boundary
+  WX<W> *X = reinterpret_cast<WX<W> *>(smem + xoff) + grp;
+  XPW<W> *xc = reinterpret_cast<XPW<W> *>(reinterpret_cast<WX<W> *>(smem + xoff) + G);
   const bool writer = warp == 0 && grp == 0;
   LaneC<1, WRT> L;
   lane_init<1, WRT>(L, T, t, idl);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(32 * W * G, MINB) wide_pose_kernel(DevTree T, 
 // B independent items: q_loss + gradient (mode 1) or one FISTA solve (mode 2); one CTA of W warps per item.
 template <int W>
 __global__ void __launch_bounds__(32 * W, 1) wide_batch_kernel(DevTree T, BatchArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   __shared__ float s_beta[BT + 1];
   if (threadIdx.x == 0) beta_table_init(s_beta);
   __syncthreads();
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(32 * W, 1) wide_batch_kernel(DevTree T, BatchA
   SlotAdr<1> sa;
   slots_init_w(co, sa, L, T, t, a.lb, a.ub);
   UniW u;
-  u.t = t; u.lane = lane; u.warp = warp; u.rounds = T.fs.rounds; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.fs_free_e >= 0;
+  u.t = t; u.lane = lane; u.warp = warp; u.grp = 0; u.rounds = T.fs.rounds; u.free_sa = T.free_sa; u.free_se = T.free_se; u.has_free = T.fs_free_e >= 0;
   u.tol = a.tol; u.maxiter = a.maxiter; u.maxls = a.maxls; u.betas = s_beta;
   const int nq = T.nq, K = T.K;
   const MaskSpec ms = {a.q_mask, nq};

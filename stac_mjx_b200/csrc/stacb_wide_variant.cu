@@ -13,8 +13,8 @@ cudaError_t FN(launch_wide_pose_, V_WW)(const DevTree &T, const PoseArgs &a, int
   int groups = 1;
   if (sched == 1 && V_WW <= 6) k = wide::wide_pose_kernel<V_WW, 8, (V_WW <= 6 ? 2 : 1), 1>;
   if (sched == 2) { k = wide::wide_pose_kernel<V_WW, 8, 1, 2>; groups = 2; }
-  const size_t smem = area_bytes + groups * sizeof(wide::WX<V_WW>) + (groups == 2 ? sizeof(wide::XPW<V_WW>) : 0);
-  if (smem > 48 * 1024) {
+  const size_t smem = area_bytes + 16 + groups * sizeof(wide::WX<V_WW>) + (groups == 2 ? sizeof(wide::XPW<V_WW>) : 0);  // + alignment slack
+  if (smem > 40 * 1024) {  // dynamic + static (momentum table, counters: ~2 KB) beyond the 48 KB default needs the opt-in
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
