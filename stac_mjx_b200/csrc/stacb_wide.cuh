@@ -29,8 +29,8 @@ struct WX {  // shared memory of one chain (16-byte aligned: poses and prefixes 
   float4 q[2][32 * W];     // pointer jumping of the world quaternions (double buffer; w, x, y, z); q[qb] holds them after the forward pass
   float4 v[2][32 * W];     // ... of the world positions (x, y, z, unused); v[vb]
   float4 wpre[32 * W][2];  // inclusive wrench prefix by lane (six values, two unused)
-  float red[2][3][W];      // warp partials of the sums over all lanes ([parity][value][warp])
-  float wsum[W][6];        // warp totals of the wrench scan
+  float4 red[2][3][2];     // warp partials of the sums over all lanes ([parity][value][warp / 4].{x,y,z,w} = warps 0..7)
+  float4 wsum[W][2];       // warp totals of the wrench scan (six values, two unused)
 };
 __device__ __forceinline__ Q4 q4_of(const float4 a) { return mk4(a.x, a.y, a.z, a.w); }
 __device__ __forceinline__ V3 v3_of(const float4 a) { return mk3(a.x, a.y, a.z); }
@@ -58,14 +58,19 @@ __device__ __forceinline__ void cta_sum(float (&val)[NV], const UniW &u, WX<W> *
   for (int i = 0; i < NV; i++) val[i] = warp_sum(val[i]);
   if (u.lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; i++) X->red[par][i][u.warp] = val[i];
+    for (int i = 0; i < NV; i++) reinterpret_cast<float *>(&X->red[par][i][0])[u.warp] = val[i];
   }
   gsync<W, G>(u);
 #pragma unroll
-  for (int i = 0; i < NV; i++) {
-    float tot = X->red[par][i][0];
-#pragma unroll
-    for (int w = 1; w < W; w++) tot = tot + X->red[par][i][w];
+  for (int i = 0; i < NV; i++) {  // the warp partials added in warp order
+    const float4 lo = X->red[par][i][0];
+    float tot = lo.x + lo.y;
+    if constexpr (W > 2) tot = (tot + lo.z) + lo.w;
+    if constexpr (W > 4) {
+      const float4 hi = X->red[par][i][1];
+      tot = (tot + hi.x) + hi.y;
+      if constexpr (W > 6) tot = (tot + hi.z) + hi.w;
+    }
     val[i] = tot;
   }
   par ^= 1;
@@ -106,17 +111,17 @@ __device__ __forceinline__ float eval_fwd(const LaneC<1, WRT> &L, const SiteC &s
   gsync<W, G>(u);
 #pragma unroll
   for (int r = 0; r < WRT; r++) {
-    if (r < u.rounds) {  // uniform
-      const Q4 Qa = q4_of(X->q[b][L.src[r]]);
-      const V3 Pa = v3_of(X->v[b][L.src[r]]);
+    if (r < u.rounds) {  // uniform; round r reads half r & 1 of the double buffers and writes the other
+      const Q4 Qa = q4_of(X->q[r & 1][L.src[r]]);
+      const V3 Pa = v3_of(X->v[r & 1][L.src[r]]);
       v = add3(Pa, rotq(v, Qa));
       Q = qmul(Qa, Q);
-      X->q[b ^ 1][t] = make_float4(Q.w, Q.x, Q.y, Q.z);
-      X->v[b ^ 1][t] = make_float4(v.x, v.y, v.z, 0.f);
+      X->q[(r & 1) ^ 1][t] = make_float4(Q.w, Q.x, Q.y, Q.z);
+      X->v[(r & 1) ^ 1][t] = make_float4(v.x, v.y, v.z, 0.f);
       gsync<W, G>(u);
-      b ^= 1;
     }
   }
+  b = u.rounds & 1;
   S.Qp = q4_of(X->q[b][L.par]);
   S.Q = Q;
   S.P = v;
@@ -146,17 +151,19 @@ __device__ __forceinline__ void eval_bwd(const LaneC<1, WRT> &L, const FwdW &S, 
     }
   }
   if (u.lane == 31) {
-#pragma unroll
-    for (int i = 0; i < 6; i++) X->wsum[u.warp][i] = w[i];
+    X->wsum[u.warp][0] = make_float4(w[0], w[1], w[2], w[3]);
+    X->wsum[u.warp][1] = make_float4(w[4], w[5], 0.f, 0.f);
   }
   gsync<W, G>(u);
   if (u.warp > 0) {  // warp-uniform
     float off[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) off[i] = X->wsum[0][i];
+    {
+      const float4 a = X->wsum[0][0], c2 = X->wsum[0][1];
+      off[0] = a.x; off[1] = a.y; off[2] = a.z; off[3] = a.w; off[4] = c2.x; off[5] = c2.y;
+    }
     for (int ww = 1; ww < u.warp; ww++) {
-#pragma unroll
-      for (int i = 0; i < 6; i++) off[i] = off[i] + X->wsum[ww][i];
+      const float4 a = X->wsum[ww][0], c2 = X->wsum[ww][1];
+      off[0] = off[0] + a.x; off[1] = off[1] + a.y; off[2] = off[2] + a.z; off[3] = off[3] + a.w; off[4] = off[4] + c2.x; off[5] = off[5] + c2.y;
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) w[i] = w[i] + off[i];
