@@ -68,6 +68,11 @@ def _worker(rank, ws, port, tmp):
     lo, hi = parallel.shard_range(C, rank, ws)
     full = parallel.allgather_blocks(clips[lo:hi].clone(), C)
     assert torch.equal(full, clips)
+    # fewer units than ranks: a rank with an empty block takes part in the collectives all the same
+    one = torch.arange(4, dtype=torch.float32).reshape(1, 4)
+    lo, hi = parallel.shard_range(1, rank, ws)
+    assert (hi - lo) == (1 if rank == 0 else 0)
+    assert torch.equal(parallel.allgather_blocks(one[lo:hi].clone(), 1), one)
     torch.save((s_all, z2_all), Path(tmp) / f"r{rank}.pt")
     dist.barrier()
     dist.destroy_process_group()
